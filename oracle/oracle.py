@@ -1,0 +1,176 @@
+"""ctypes loader of the CPU oracle (oracle/cvo_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under cvo_slam_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from cvo_slam_b200.capi import (Calib, LowLevel, Params, CVO_OK)  # noqa: E402  (struct layouts only)
+
+LIB = os.path.join(HERE, "libcvo_oracle.so")
+LIB_KD = os.path.join(HERE, "_ref", "libcvo_oracle_kd.so")
+
+SEARCH_GRID, SEARCH_BRUTE, SEARCH_NANOFLANN = 0, 1, 2
+
+
+def build(force=False):
+    """Compile the oracle (and, where /root/reference exists, the nanoflann variant)."""
+    src = os.path.join(HERE, "cvo_oracle.cpp")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "all"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/thirdparty/cvo/thirdparty/nanoflann.hpp"):
+        if force or not os.path.exists(LIB_KD) or os.path.getmtime(LIB_KD) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+class OracleLowLevel(LowLevel):
+    def __init__(self, lib):
+        super().__init__(lib, "oracle_")
+        P = C.POINTER
+        vp = C.c_void_p
+        lib.oracle_create.argtypes = [P(Calib), P(Params), P(vp)]
+        lib.oracle_set_search.argtypes = [vp, C.c_int]
+        lib.oracle_stats.argtypes = [vp, P(C.c_int64)]
+        lib.oracle_gray.argtypes = [vp, C.c_int, C.c_int, vp]
+        lib.oracle_hsv.argtypes = [vp, C.c_int, vp]
+        lib.oracle_stages.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+        lib.oracle_random_pattern.argtypes = [vp, C.c_int]
+        lib.oracle_cubic_real_roots.argtypes = [C.c_double] * 4 + [P(C.c_double)]
+        lib.oracle_step_from_coeffs.argtypes = [C.c_double] * 4 + [C.c_float, C.c_float]
+        lib.oracle_step_from_coeffs.restype = C.c_float
+        lib.oracle_exp_sek3.argtypes = [P(C.c_float), P(C.c_float), C.c_float, P(C.c_float), P(C.c_float)]
+        lib.oracle_dist_se3.argtypes = [P(C.c_float), P(C.c_float)]
+        lib.oracle_dist_se3.restype = C.c_float
+        lib.oracle_finish_hessian.argtypes = [P(C.c_float), C.c_int, P(C.c_double)]
+        lib.oracle_radius_search.argtypes = [P(C.c_float), C.c_int, P(C.c_float), C.c_float, C.c_int,
+                                             P(C.c_int32), P(C.c_float), C.c_int]
+        lib.oracle_set_num_threads.argtypes = [C.c_int]
+        self.has_nanoflann = bool(lib.oracle_has_nanoflann())
+        self.search_mode = SEARCH_NANOFLANN if self.has_nanoflann else SEARCH_GRID
+
+    def num_threads(self):
+        return int(self.lib.oracle_num_threads())
+
+    def set_num_threads(self, n):
+        self.lib.oracle_set_num_threads(int(n))
+
+    def create(self, calib, params=None, device=0, search=None):
+        if params is None:
+            params = self.default_params()
+        h = C.c_void_p()
+        self._check(self.lib.oracle_create(C.byref(calib), C.byref(params), C.byref(h)), "create")
+        self.lib.oracle_set_search(h, self.search_mode if search is None else search)
+        return h
+
+    def set_search(self, h, mode):
+        self.lib.oracle_set_search(h, mode)
+
+    def stats(self, h):
+        s = (C.c_int64 * 3)()
+        self.lib.oracle_stats(h, s)
+        return dict(launches=0, evals=s[1], iterations=s[2])
+
+    # ---- stage-level helpers -------------------------------------------------------------
+    def gray(self, bgr, mode=0):
+        bgr = np.ascontiguousarray(bgr, np.uint8).reshape(-1, 3)
+        out = np.zeros(len(bgr), np.uint8)
+        self.lib.oracle_gray(bgr.ctypes.data, len(bgr), mode, out.ctypes.data)
+        return out
+
+    def hsv(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8).reshape(-1, 3)
+        out = np.zeros((len(bgr), 3), np.uint8)
+        self.lib.oracle_hsv(bgr.ctypes.data, len(bgr), out.ctypes.data)
+        return out
+
+    def stages(self, bgr, gray_mode=0):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        h, w, _ = bgr.shape
+        sizes = [w * h, (w // 2) * (h // 2), (w // 4) * (h // 4)]
+        gray = np.zeros((h, w), np.uint8)
+        g2 = np.zeros(sum(sizes), np.float32)
+        nb = (w // 32) * (h // 32)
+        ths = np.zeros(nb, np.float32)
+        thss = np.zeros(nb, np.float32)
+        dx0 = np.zeros((h, w), np.float32)
+        dy0 = np.zeros((h, w), np.float32)
+        self.lib.oracle_stages(bgr.ctypes.data, w, h, gray_mode, gray.ctypes.data, g2.ctypes.data,
+                               ths.ctypes.data, thss.ctypes.data, dx0.ctypes.data, dy0.ctypes.data)
+        lv = [g2[:sizes[0]].reshape(h, w),
+              g2[sizes[0]:sizes[0] + sizes[1]].reshape(h // 2, w // 2),
+              g2[sizes[0] + sizes[1]:].reshape(h // 4, w // 4)]
+        return dict(gray=gray, g2=lv, ths=ths.reshape(h // 32, w // 32),
+                    ths_smoothed=thss.reshape(h // 32, w // 32), dx0=dx0, dy0=dy0)
+
+    def random_pattern(self, n):
+        out = np.zeros(n, np.uint8)
+        self.lib.oracle_random_pattern(out.ctypes.data, n)
+        return out
+
+    def cubic_real_roots(self, a, b, c, d):
+        re = (C.c_double * 3)()
+        n = self.lib.oracle_cubic_real_roots(a, b, c, d, re)
+        return [re[i] for i in range(n)]
+
+    def step_from_coeffs(self, B, Cc, D, E, min_step=0.2, max_step=0.8):
+        return float(self.lib.oracle_step_from_coeffs(B, Cc, D, E, min_step, max_step))
+
+    def exp_sek3(self, w, v, dt):
+        w = np.ascontiguousarray(w, np.float32)
+        v = np.ascontiguousarray(v, np.float32)
+        R = np.zeros(9, np.float32)
+        t = np.zeros(3, np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        self.lib.oracle_exp_sek3(fp(w), fp(v), float(dt), fp(R), fp(t))
+        return R.reshape(3, 3), t
+
+    def dist_se3(self, R, T):
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        T = np.ascontiguousarray(T, np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        return float(self.lib.oracle_dist_se3(fp(R), fp(T)))
+
+    def finish_hessian(self, Hf, inliers):
+        Hf = np.ascontiguousarray(Hf, np.float32).reshape(36)
+        out = np.zeros(36, np.float64)
+        self.lib.oracle_finish_hessian(Hf.ctypes.data_as(C.POINTER(C.c_float)), int(inliers),
+                                       out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out.reshape(6, 6)
+
+    def radius_search(self, pts, q, radius2, mode):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        q = np.ascontiguousarray(q, np.float32)
+        cap = len(pts)
+        idx = np.zeros(cap, np.int32)
+        d2 = np.zeros(cap, np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+        n = self.lib.oracle_radius_search(fp(pts), len(pts), fp(q), float(radius2), mode,
+                                          idx.ctypes.data_as(C.POINTER(C.c_int32)), fp(d2), cap)
+        return idx[:n], d2[:n]
+
+
+_cache = {}
+
+
+def load(kd=None):
+    """kd=True: the oracle/_ref build whose radius search is the reference's nanoflann;
+    kd=False: the self-contained build; kd=None: nanoflann when available."""
+    build()
+    if kd is None:
+        kd = os.path.exists(LIB_KD)
+    path = LIB_KD if kd else LIB
+    if path not in _cache:
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not built")
+        _cache[path] = OracleLowLevel(C.CDLL(path))
+    return _cache[path]
