@@ -1,0 +1,99 @@
+"""Batches of independent frame pairs (the loop-closure verification pattern of
+src/keyframe_graph.cpp:622-731: a fresh cvo object per candidate, `reset_initial` prior,
+set_pcd x2, align, inner product) through the C ABI's cvo_batch_* entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Batch:
+    def __init__(self, calib, params=None, max_frames=64, max_pairs=64, width=640, height=480,
+                 device=0, api=None):
+        self.api = api if api is not None else capi.load()
+        self.lib = self.api.lib
+        self.params = params if params is not None else self.api.default_params()
+        self.w, self.h = width, height
+        self.max_frames, self.max_pairs = max_frames, max_pairs
+        self.b = C.c_void_p()
+        self.api._check(self.lib.cvo_batch_create(C.byref(calib), C.byref(self.params), device,
+                                                  max_frames, max_pairs, width, height,
+                                                  C.byref(self.b)), "batch_create")
+
+    def close(self):
+        if self.b:
+            self.lib.cvo_batch_destroy(self.b)
+            self.b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- frames ------------------------------------------------------------------------------
+    def set_frames(self, bgr, depth, first=0):
+        """bgr [n,h,w,3] uint8, depth [n,h,w] uint16 host arrays (pinned memory makes the copies async)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        n = bgr.shape[0]
+        assert bgr.shape == (n, self.h, self.w, 3) and depth.shape == (n, self.h, self.w)
+        self.api._check(self.lib.cvo_batch_set_frames(self.b, first, n, bgr.ctypes.data,
+                                                      depth.ctypes.data), "batch_set_frames")
+
+    def set_frames_ptr(self, bgr_ptr, depth_ptr, n, first=0, device=False):
+        fn = self.lib.cvo_batch_set_frames_device if device else self.lib.cvo_batch_set_frames
+        self.api._check(fn(self.b, first, n, bgr_ptr, depth_ptr), "batch_set_frames")
+
+    def frame_size(self, k):
+        n = C.c_int(0)
+        self.api._check(self.lib.cvo_batch_frame_size(self.b, k, C.byref(n)), "batch_frame_size")
+        return n.value
+
+    # ---- pairs -------------------------------------------------------------------------------
+    def make_pairs(self, pairs, R=None, T=None, ell=None):
+        """pairs: iterable of (fixed_frame, moving_frame); optional per-pair initial R [n,3,3],
+        T [n,3] (e.g. from reset_initial) and ell.  Fresh-object defaults otherwise."""
+        pairs = np.asarray(list(pairs), dtype=np.int32).reshape(-1, 2)
+        n = len(pairs)
+        d = np.zeros(n, dtype=capi.PAIR_DTYPE)
+        d["fixed_frame"] = pairs[:, 0]
+        d["moving_frame"] = pairs[:, 1]
+        d["R"] = np.eye(3, dtype=np.float32).reshape(9) if R is None else np.asarray(R, np.float32).reshape(n, 9)
+        d["T"] = 0 if T is None else np.asarray(T, np.float32).reshape(n, 3)
+        d["ell"] = self.params.ell_init if ell is None else ell
+        return d
+
+    def align(self, pairs, R=None, T=None, ell=None):
+        d = pairs if isinstance(pairs, np.ndarray) and pairs.dtype == capi.PAIR_DTYPE \
+            else self.make_pairs(pairs, R, T, ell)
+        res = np.zeros(len(d), dtype=capi.RESULT_DTYPE)
+        self.api._check(self.lib.cvo_batch_align(self.b, len(d), d.ctypes.data, res.ctypes.data),
+                        "batch_align")
+        self._last_pairs = d
+        return res
+
+    def inner_product(self, pairs, results):
+        d = pairs if isinstance(pairs, np.ndarray) and pairs.dtype == capi.PAIR_DTYPE \
+            else self.make_pairs(pairs)
+        vals = np.zeros(len(d), np.float32)
+        nums = np.zeros(len(d), np.int32)
+        res = np.ascontiguousarray(results)
+        self.api._check(self.lib.cvo_batch_inner_product(self.b, len(d), d.ctypes.data, res.ctypes.data,
+                                                         vals.ctypes.data, nums.ctypes.data),
+                        "batch_inner_product")
+        return vals, nums
+
+    def stats(self):
+        s = (C.c_int64 * 3)()
+        self.api._check(self.lib.cvo_batch_stats(self.b, s), "batch_stats")
+        return dict(launches=s[0], evals=s[1], iterations=s[2])
+
+    def last_align_ms(self):
+        ms = C.c_float(0)
+        self.api._check(self.lib.cvo_batch_last_align_ms(self.b, C.byref(ms)), "batch_last_align_ms")
+        return ms.value

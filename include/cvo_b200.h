@@ -129,6 +129,10 @@ int cvo_align(cvo_handle *h, cvo_align_result *out, cvo_iter_record *trace, int 
 int cvo_iteration_at(cvo_handle *h, const float R[9], const float T[3], float ell,
                      cvo_iter_record *out);
 
+/* in-cutoff pattern (i = fixed index, j = moving index, a_ij) of the last cvo_iteration_at /
+ * cvo_align iteration, unordered; n receives the total count.  Test hook. */
+int cvo_last_pattern(cvo_handle *h, int32_t *ij, float *a, int cap, int *n);
+
 /* replaces cvo::function_inner_product (cvo.cpp:388-459) for <Ta*slot_a, slot_b> at the
  * handle's current ell.  Ta = 3x4 row-major [R|t] applied to slot_a, or NULL. */
 int cvo_inner_product(cvo_handle *h, int slot_a, const float *Ta, int slot_b, float *value,

@@ -1,0 +1,385 @@
+"""Parity of the CUDA path (libcvo_b200.so, through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star / SURVEY §8d "Parity gates"):
+  * point selection, pixel coordinates, positions, features: bit-exact
+  * in-cutoff pattern at an injected (R, T, ell): identical except ties |a - sp|/sp < 1e-5
+  * omega, v: 1e-5 relative; B..E, step: 1e-4 relative (fp32 terms, fp64 sums)
+  * final pose after the same schedule: 1e-4 rad / 1e-4 m
+  * inner products: 1e-4 relative; Hessian: 1e-4 of its largest entry
+"""
+import numpy as np
+import pytest
+
+from conftest import pose_error
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_RAD = 1e-4
+POSE_TOL_M = 1e-4
+INNER_RTOL = 1e-4
+
+
+def _calib_of(g):
+    from cvo_slam_b200 import capi
+    return capi.Calib(*[float(x) for x in g["calib"]])
+
+
+def _both(cuda_api, oracle_api, calib, params=None):
+    return cuda_api.create(calib, params), oracle_api.create(calib, params)
+
+
+def test_library_and_random_pattern(cuda_api, oracle_api):
+    n = 640 * 480
+    assert np.array_equal(cuda_api.random_pattern(n), oracle_api.random_pattern(n))
+
+
+def _check_selection(cuda_api, oracle_api, calib, bgr, depth, params=None):
+    hc, ho = _both(cuda_api, oracle_api, calib, params)
+    h, w = depth.shape
+    cuda_api.set_frame(hc, 0, bgr, depth)
+    oracle_api.set_frame(ho, 0, bgr, depth)
+    mo, io = oracle_api.get_selection_debug(ho, 0, w, h)
+    mc, ic = cuda_api.get_selection_debug(hc, 0, w, h)
+    assert ic == io
+    assert np.array_equal(mc, mo), f"{int((mc != mo).sum())} status-map pixels differ"
+    assert cuda_api.slot_size(hc, 0) == oracle_api.slot_size(ho, 0)
+    assert np.array_equal(cuda_api.get_selected_points(hc, 0), oracle_api.get_selected_points(ho, 0))
+    pc, fc = cuda_api.get_cloud(hc, 0)
+    po, fo = oracle_api.get_cloud(ho, 0)
+    assert np.array_equal(pc.view(np.uint32), po.view(np.uint32))
+    assert np.array_equal(fc.view(np.uint32), fo.view(np.uint32))
+    n = len(pc)
+    cuda_api.destroy(hc)
+    oracle_api.destroy(ho)
+    return n, io
+
+
+def test_selection_bit_exact_c1(cuda_api, oracle_api, tum_calib, pair_c1):
+    bgr_a, d_a, bgr_b, d_b, _ = pair_c1
+    for bgr, d in ((bgr_a, d_a), (bgr_b, d_b)):
+        n, info = _check_selection(cuda_api, oracle_api, tum_calib, bgr, d)
+        assert 2000 < n < 3400
+
+
+def test_selection_bit_exact_golden(cuda_api, golden_small):
+    g = golden_small
+    h = cuda_api.create(_calib_of(g))
+    cuda_api.set_frame(h, 0, g["bgr_a"], g["depth_a"])
+    m, info = cuda_api.get_selection_debug(h, 0, 640, 480)
+    assert np.array_equal(np.flatnonzero(m), g["map_idx_a"])
+    assert np.array_equal(m.reshape(-1)[g["map_idx_a"]], g["map_val_a"])
+    assert [info[k] for k in ("n2", "n3", "n4", "pot", "passes")] == g["sel_info_a"].tolist()
+    pos, feat = cuda_api.get_cloud(h, 0)
+    assert np.array_equal(pos, g["pos_a"]) and np.array_equal(feat, g["feat_a"])
+    assert np.array_equal(cuda_api.get_selected_points(h, 0), g["pix_a"])
+    cuda_api.destroy(h)
+
+
+def test_selection_eth3d_shape_odd_width(cuda_api, oracle_api):
+    """739 x 458: odd-width pyramid stride quirk and the out-of-range threshold rows."""
+    from cvo_slam_b200 import capi, synth
+    cal = capi.ETH3D_CALIB()
+    scene = synth.make_scene(4)
+    bgr, d = synth.to_numpy(*synth.render(scene, synth.pose(), cal, 739, 458, noise_seed=4))
+    n, info = _check_selection(cuda_api, oracle_api, cal, bgr, d)
+    assert n > 1500
+
+
+def test_selection_dense_and_sparse_recursion(cuda_api, oracle_api, tum_calib):
+    """num_want = 60000 drives the selector to pot = 1 (quotia > 1.25); num_want = 300 to a larger
+    pot (quotia < 0.25) — both branches of makeMaps' recursion (PixelSelector2.cpp:193-223)."""
+    from cvo_slam_b200 import synth
+    scene = synth.make_scene(3, high_gradient=True)
+    bgr, d = synth.to_numpy(*synth.render(scene, synth.pose(), tum_calib, 640, 480, noise_seed=3))
+    p = cuda_api.default_params()
+    p.num_want = 60000
+    n, info = _check_selection(cuda_api, oracle_api, tum_calib, bgr, d, p)
+    assert info["passes"] == 2 and info["pot"] == 1 and n > 8000
+    p.num_want = 300
+    n, info = _check_selection(cuda_api, oracle_api, tum_calib, bgr, d, p)
+    assert info["passes"] == 2 and info["pot"] > 3
+
+
+def test_selection_feature_type0_and_gray14(cuda_api, oracle_api, tum_calib, pair_c1):
+    bgr_a, d_a = pair_c1[0], pair_c1[1]
+    p = cuda_api.default_params()
+    p.feature_type = 0
+    _check_selection(cuda_api, oracle_api, tum_calib, bgr_a, d_a, p)
+    p = cuda_api.default_params()
+    p.gray_mode = 1
+    _check_selection(cuda_api, oracle_api, tum_calib, bgr_a, d_a, p)
+
+
+def test_selection_flat_image_selects_nothing(cuda_api, oracle_api, tum_calib):
+    bgr = np.full((480, 640, 3), 90, np.uint8)
+    d = np.full((480, 640), 5000, np.uint16)
+    n, info = _check_selection(cuda_api, oracle_api, tum_calib, bgr, d)
+    assert n == 0
+
+
+def _pattern_keys(ij):
+    return ij[:, 0].astype(np.int64) * (1 << 20) + ij[:, 1].astype(np.int64)
+
+
+def _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, sp=8e-3):
+    rc = cuda_api.iteration_at(hc, R, T, ell)
+    ro = oracle_api.iteration_at(ho, R, T, ell)
+    ijc, ac, nc = cuda_api.last_pattern(hc, 1 << 20)
+    ijo, ao, no = oracle_api.last_pattern(ho, 1 << 20)
+    assert nc == len(ac) == rc["nnz"] and no == ro["nnz"]
+    kc, ko = _pattern_keys(ijc), _pattern_keys(ijo)
+    oc, oo = np.argsort(kc), np.argsort(ko)
+    kc, ac, ko, ao = kc[oc], ac[oc], ko[oo], ao[oo]
+    only_c = np.setdiff1d(kc, ko, assume_unique=True)
+    only_o = np.setdiff1d(ko, kc, assume_unique=True)
+    # documented cutoff ties: MUFU ex2 vs double exp can flip `a > sp_thres` within 1e-5 relative
+    for k in only_c:
+        assert abs(ac[np.searchsorted(kc, k)] - sp) / sp < 1e-5
+    for k in only_o:
+        assert abs(ao[np.searchsorted(ko, k)] - sp) / sp < 1e-5
+    ties = len(only_c) + len(only_o)
+    assert ties <= max(3, no // 2000), (ties, no)
+    common = np.intersect1d(kc, ko, assume_unique=True)
+    a_c = ac[np.searchsorted(kc, common)]
+    a_o = ao[np.searchsorted(ko, common)]
+    assert np.allclose(a_c, a_o, rtol=3e-6, atol=0)
+    scale_w = max(np.abs(ro["omega"]).max(), 1e-6)
+    scale_v = max(np.abs(ro["v"]).max(), 1e-6)
+    assert np.allclose(rc["omega"], ro["omega"], rtol=1e-5, atol=2e-5 * scale_w)
+    assert np.allclose(rc["v"], ro["v"], rtol=1e-5, atol=2e-5 * scale_v)
+    for key in "BCDE":
+        assert rc[key] == pytest.approx(ro[key], rel=1e-4, abs=1e-4 * max(abs(ro["B"]), 1e-9)), key
+    assert rc["step"] == pytest.approx(ro["step"], rel=1e-4)
+    return ties, no
+
+
+def test_iteration_parity_golden(cuda_api, oracle_api, golden_small):
+    g = golden_small
+    hc, ho = _both(cuda_api, oracle_api, _calib_of(g))
+    for api, h in ((cuda_api, hc), (oracle_api, ho)):
+        api.set_cloud(h, 0, g["pos_a"], g["feat_a"])
+        api.set_cloud(h, 1, g["pos_b"], g["feat_b"])
+    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    total_ties = 0
+    for ell in (0.15, 0.10, 0.06, 0.03):
+        ties, n = _check_iteration(cuda_api, oracle_api, hc, ho, I, z, ell)
+        total_ties += ties
+    # states near the solution: (R, T) = inverse of the oracle's final transform, perturbed
+    Tf = g["align_transform"].astype(np.float64)
+    rng = np.random.default_rng(0)
+    for k in range(4):
+        from cvo_slam_b200 import synth
+        P = synth.pose(rng.normal(0, 2e-3, 3), rng.normal(0, 2e-3, 3))
+        M = np.linalg.inv(Tf @ P)
+        ties, n = _check_iteration(cuda_api, oracle_api, hc, ho, M[:3, :3].astype(np.float32),
+                                   M[:3, 3].astype(np.float32), (0.10, 0.06, 0.03, 0.03)[k])
+        total_ties += ties
+    # golden vectors (made with the reference's nanoflann): nnz at the identity state
+    rec = cuda_api.iteration_at(hc, I, z, 0.15)
+    assert abs(rec["nnz"] - int(g["it0_nnz"])) <= 2
+    assert np.allclose(rec["omega"], g["it0_omega"], rtol=1e-5, atol=1e-5 * np.abs(g["it0_omega"]).max())
+    print("cutoff ties over 8 injected states:", total_ties)
+    cuda_api.destroy(hc)
+    oracle_api.destroy(ho)
+
+
+def test_align_parity_golden(cuda_api, golden_small):
+    g = golden_small
+    h = cuda_api.create(_calib_of(g))
+    cuda_api.set_frame(h, 0, g["bgr_a"], g["depth_a"])
+    cuda_api.set_frame(h, 1, g["bgr_b"], g["depth_b"])
+    res, recs = cuda_api.align(h, trace_cap=2000)
+    ang, dist = pose_error(res.transform_np(), g["align_transform"])
+    print("golden: iterations gpu/oracle", res.iterations, int(g["align_scalars"][0]), "pose diff", ang, dist)
+    assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    assert res.status == 0
+    assert res.ell == pytest.approx(float(g["align_ell"]))
+    assert abs(res.iterations - int(g["align_scalars"][0])) <= 10     # reported, loosely bounded
+    n = min(len(recs), len(g["trace_nnz"]), 21)
+    assert np.array_equal([r["ell"] for r in recs[:n]], g["trace_ell"][:n])
+    # early iterations follow the oracle's trajectory closely
+    for k in range(4):
+        assert np.allclose(recs[k]["omega"], g["trace_omega"][k], rtol=1e-3, atol=1e-4)
+        assert abs(recs[k]["nnz"] - g["trace_nnz"][k]) <= max(3, g["trace_nnz"][k] // 1000)
+    # queries at the final state
+    T = res.transform_np()
+    vals = [cuda_api.inner_product(h, 1, None, 0), cuda_api.inner_product(h, 1, T, 0),
+            cuda_api.inner_product(h, 0, None, 0), cuda_api.inner_product(h, 1, None, 1)]
+    for (v, n_), gv, gn, name in zip(vals, g["inner_values"], g["inner_nums"], ("pre", "post", "fixed", "moving")):
+        if name == "post":     # evaluated at slightly different final poses
+            assert v == pytest.approx(float(gv), rel=5e-3)
+        else:
+            assert v == pytest.approx(float(gv), rel=INNER_RTOL), name
+            assert n_ == int(gn), name
+    cuda_api.destroy(h)
+
+
+def test_queries_parity_same_pose(cuda_api, oracle_api, golden_small):
+    """inner products and Hessian at exactly the same transform and ell on both sides."""
+    g = golden_small
+    hc, ho = _both(cuda_api, oracle_api, _calib_of(g))
+    for api, h in ((cuda_api, hc), (oracle_api, ho)):
+        api.set_cloud(h, 0, g["pos_a"], g["feat_a"])
+        api.set_cloud(h, 1, g["pos_b"], g["feat_b"])
+    T = g["align_transform"]
+    for ell in (0.15, 0.03):
+        cuda_api.set_ell(hc, ell)
+        oracle_api.set_ell(ho, ell)
+        for sa, Ta, sb in ((1, None, 0), (1, T, 0), (0, None, 0), (1, None, 1)):
+            vc, nc = cuda_api.inner_product(hc, sa, Ta, sb)
+            vo, no = oracle_api.inner_product(ho, sa, Ta, sb)
+            assert nc == no
+            assert vc == pytest.approx(vo, rel=INNER_RTOL)
+        Hc, ic = cuda_api.hessian(hc, 1, T, 0)
+        Ho, io = oracle_api.hessian(ho, 1, T, 0)
+        assert ic == io
+        assert np.allclose(Hc, Ho, rtol=0, atol=1e-4 * np.abs(Ho).max())
+        assert np.allclose(Hc, Hc.T)
+    cuda_api.destroy(hc)
+    oracle_api.destroy(ho)
+
+
+def test_align_parity_c1(cuda_api, oracle_api, tum_calib, pair_c1):
+    bgr_a, d_a, bgr_b, d_b, T_gt = pair_c1
+    hc, ho = _both(cuda_api, oracle_api, tum_calib)
+    for api, h in ((cuda_api, hc), (oracle_api, ho)):
+        api.set_frame(h, 0, bgr_a, d_a)
+        api.set_frame(h, 1, bgr_b, d_b)
+    rc, _ = cuda_api.align(hc)
+    ro, _ = oracle_api.align(ho)
+    ang, dist = pose_error(rc.transform_np(), ro.transform_np())
+    print("C1: iterations gpu/oracle", rc.iterations, ro.iterations, "pose diff", ang, dist)
+    assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    ang, dist = pose_error(rc.transform_np(), T_gt)
+    assert ang < 5e-3 and dist < 5e-3
+    # state persists: a second align of the same object starts from R, T, ell left behind
+    assert cuda_api.get_ell(hc) == pytest.approx(oracle_api.get_ell(ho))
+    Rc, Tc = cuda_api.get_RT(hc)
+    assert np.allclose(Rc, rc.R_np()) and np.allclose(Tc, rc.T_np())
+    rc2, _ = cuda_api.align(hc)
+    ro2, _ = oracle_api.align(ho)
+    ang, dist = pose_error(rc2.transform_np(), ro2.transform_np())
+    assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    cuda_api.destroy(hc)
+    oracle_api.destroy(ho)
+
+
+def test_align_eth3d_large_ell(cuda_api, oracle_api):
+    """C4: 739x458 pair, larger motion, default and ell_init = 0.25 (wide cutoff, many neighbours)."""
+    from cvo_slam_b200 import capi, synth
+    cal = capi.ETH3D_CALIB()
+    a, da, b, db, T_gt = synth.make_pair(4, cal, w=739, h=458, rot_deg=2.0, trans=(0.04, -0.02, 0.03))
+    for ell in (None, 0.25):
+        p = cuda_api.default_params()
+        if ell:
+            p.ell_init = ell
+        hc, ho = _both(cuda_api, oracle_api, cal, p)
+        for api, h in ((cuda_api, hc), (oracle_api, ho)):
+            api.set_frame(h, 0, a, da)
+            api.set_frame(h, 1, b, db)
+        rc, _ = cuda_api.align(hc)
+        ro, _ = oracle_api.align(ho)
+        assert rc.status == 0
+        ang, dist = pose_error(rc.transform_np(), ro.transform_np())
+        print("C4 ell", ell, "iterations", rc.iterations, ro.iterations, "pose diff", ang, dist)
+        assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+        cuda_api.destroy(hc)
+        oracle_api.destroy(ho)
+
+
+def test_edge_cases(cuda_api, oracle_api, tum_calib):
+    from cvo_slam_b200.capi import CvoError
+    h = cuda_api.create(tum_calib)
+    with pytest.raises(CvoError):
+        cuda_api.align(h)                      # "cvo not initialized !" -> CVO_ERR_NOT_INIT
+    rng = np.random.default_rng(7)
+    a = rng.uniform(0, 1, (50, 3)).astype(np.float32)
+    f = rng.uniform(0, 255, (50, 5)).astype(np.float32)
+    cuda_api.set_cloud(h, 0, a, f)
+    cuda_api.set_cloud(h, 1, a + 10.0, f)      # far apart: empty neighbourhoods
+    res, recs = cuda_api.align(h, trace_cap=4)
+    assert res.iterations == 1 and res.iter == 0 and res.A_nonzero == 0
+    assert recs[0]["step"] == pytest.approx(0.2)
+    assert np.array_equal(res.transform_np(), np.eye(4, dtype=np.float32))
+    v, n = cuda_api.inner_product(h, 1, None, 0)
+    assert v == 0 and n == 1
+    Hm, inl = cuda_api.hessian(h, 1, None, 0)
+    assert inl == 0 and np.array_equal(Hm, np.eye(6))
+    # empty cloud
+    cuda_api.set_cloud(h, 1, np.zeros((0, 3), np.float32), np.zeros((0, 5), np.float32))
+    res, _ = cuda_api.align(h)
+    assert res.A_nonzero == 0 and res.iterations == 1
+    # ragged sizes, identical clouds: zero flow at the optimum of <x, x>? not zero, but finite
+    cuda_api.set_cloud(h, 1, a[:17], f[:17])
+    res, _ = cuda_api.align(h)
+    assert np.isfinite(res.transform_np()).all()
+    # slot moves
+    cuda_api.slot_move(h, 2, 1)
+    assert cuda_api.slot_size(h, 1) == -1 and cuda_api.slot_size(h, 2) == 17
+    cuda_api.destroy(h)
+
+
+def test_batch_matches_single_and_oracle(cuda_api, oracle_api, tum_calib):
+    import ctypes as C
+    from cvo_slam_b200 import batch as B, synth
+    scene = synth.make_scene(5)
+    rng = np.random.default_rng(5)
+    frames = []
+    poses = [synth.pose()] + [synth.pose(rng.normal(0, 6e-3, 3), rng.normal(0, 8e-3, 3)) for _ in range(3)]
+    for k, P in enumerate(poses):
+        frames.append(synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=50 + k)))
+    bgr = np.stack([f[0] for f in frames])
+    dep = np.stack([f[1] for f in frames])
+    pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (2, 3), (3, 1), (1, 0)]
+    bt = B.Batch(tum_calib, max_frames=4, max_pairs=len(pairs), width=640, height=480)
+    bt.set_frames(bgr, dep)
+    sizes = [bt.frame_size(k) for k in range(4)]
+    res = bt.align(pairs)
+    vals, nums = bt.inner_product(pairs, res)
+    assert all(r["status"] == 0 for r in res)
+    for (fi, mi), r, v in zip(pairs, res, vals):
+        ho = oracle_api.create(tum_calib)
+        oracle_api.set_frame(ho, 0, *frames[fi])
+        oracle_api.set_frame(ho, 1, *frames[mi])
+        assert oracle_api.slot_size(ho, 0) == sizes[fi]
+        ro, _ = oracle_api.align(ho)
+        ang, dist = pose_error(r["transform"].reshape(4, 4), ro.transform_np())
+        assert ang < POSE_TOL_RAD and dist < POSE_TOL_M, (fi, mi, ang, dist)
+        gt = synth.relative_transform(poses[fi], poses[mi])
+        ang, dist = pose_error(r["transform"].reshape(4, 4), gt)
+        assert ang < 6e-3 and dist < 6e-3
+        vo, _ = oracle_api.inner_product(ho, 1, ro.transform_np(), 0)
+        assert v == pytest.approx(vo, rel=5e-3)
+        oracle_api.destroy(ho)
+    # the batch path and the handle path run the same kernel: identical bits
+    hc = cuda_api.create(tum_calib)
+    cuda_api.set_frame(hc, 0, *frames[0])
+    cuda_api.set_frame(hc, 1, *frames[1])
+    rs, _ = cuda_api.align(hc)
+    assert np.array_equal(rs.transform_np().reshape(-1), res[0]["transform"])
+    cuda_api.destroy(hc)
+    st = bt.stats()
+    assert st["launches"] > 0 and st["evals"] > 0
+    bt.close()
+
+
+def test_tracking_sequence_parity(cuda_api, oracle_api, tum_calib):
+    """C2 in miniature: the LocalTracker call pattern over 6 frames, two cvo objects with
+    persistent R/T/ell, GPU vs oracle."""
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    scene = synth.make_scene(2)
+    poses = synth.trajectory(6, 2)
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=20 + k))
+              for k, P in enumerate(poses)]
+    out_c = cvo_mod.track_sequence(frames, tum_calib, api=cuda_api)
+    out_o = cvo_mod.track_sequence(frames, tum_calib, api=oracle_api)
+    for k, (c, o) in enumerate(zip(out_c, out_o)):
+        for key in ("odometry", "keyframe"):
+            ang, dist = pose_error(c[key], o[key])
+            assert ang < POSE_TOL_RAD and dist < POSE_TOL_M, (k, key, ang, dist)
+        for key in ("inn_pre", "inn_fixed_pcd", "inn_moving_pcd"):
+            assert c["r_odometry"][key].value == pytest.approx(o["r_odometry"][key].value, rel=INNER_RTOL)
+        assert c["r_odometry"]["inn_post"].value == pytest.approx(o["r_odometry"]["inn_post"].value, rel=5e-3)
+        assert c["r_odometry"]["cos_angle"] == pytest.approx(o["r_odometry"]["cos_angle"], rel=5e-3)
+        Hc, Ho = c["r_odometry"]["post_hessian"], o["r_odometry"]["post_hessian"]
+        assert np.allclose(Hc, Ho, rtol=0, atol=2e-2 * np.abs(Ho).max())

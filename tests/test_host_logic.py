@@ -1,0 +1,143 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every
+symbol include/cvo_b200.h declares (no compute without a GPU), struct layouts match, and
+the host-side mirror of cvo::cvo drives the oracle correctly through the state shuffles
+of cvo.cpp:578-618."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pose_error
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "cvo_b200.h")).read()
+
+
+@pytest.fixture(scope="module")
+def cuda_lib_path():
+    from cvo_slam_b200 import build, capi
+    build.build()
+    return capi.LIB_PATH
+
+
+def test_library_exports_every_declared_symbol(cuda_lib_path):
+    lib = C.CDLL(cuda_lib_path)
+    names = sorted(set(re.findall(r"\b(cvo_[a-z_A-Z0-9]+)\s*\(", _header())))
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_library_is_sm100a_with_lineinfo(cuda_lib_path):
+    out = subprocess.run(["cuobjdump", "-lelf", cuda_lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_header(cuda_lib_path):
+    """sizeof() as the C compiler sees the header vs the ctypes mirrors."""
+    from cvo_slam_b200 import capi
+    src = '#include "cvo_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(cvo_calib),sizeof(cvo_params),sizeof(cvo_align_result),sizeof(cvo_iter_record),sizeof(cvo_pair_desc));}'
+    exe = "/tmp/_cvo_sizes"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src.encode(), check=True)
+    got = [int(x) for x in subprocess.check_output([exe]).split()]
+    want = [C.sizeof(capi.Calib), C.sizeof(capi.Params), C.sizeof(capi.AlignResult),
+            C.sizeof(capi.IterRecord), C.sizeof(capi.PairDesc)]
+    assert got == want
+
+
+def test_default_params_match_reference_constants(cuda_lib_path, oracle_plain):
+    from cvo_slam_b200 import capi
+    lib = C.CDLL(cuda_lib_path)
+    p = capi.Params()
+    lib.cvo_default_params(C.byref(p))
+    q = oracle_plain.default_params()
+    for name, _ in capi.Params._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    assert (p.ell_init, p.max_iter, p.num_want, p.feature_type) == (np.float32(0.15), 2000, 3000, 1)
+
+
+def test_random_pattern_restatement_matches_libc(cuda_lib_path, oracle_plain):
+    """cvo_random_pattern restates glibc's TYPE_3 rand(); the oracle calls libc itself."""
+    lib = C.CDLL(cuda_lib_path)
+    n = 739 * 458
+    out = np.zeros(n, np.uint8)
+    assert lib.cvo_random_pattern(C.c_void_p(out.ctypes.data), n) == 0
+    assert np.array_equal(out, oracle_plain.random_pattern(n))
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "cvo_slam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "cvo_oracle" not in txt, f
+
+
+def test_cvo_mirror_state_shuffles(oracle_plain, tum_calib):
+    """update_fixed_pcd / update_previous_pcd / reset_keyframe / reset_initial semantics
+    (cvo.cpp:578-618) through the Python mirror, driven by the oracle back end."""
+    from cvo_slam_b200 import cvo as cvo_mod
+    rng = np.random.default_rng(0)
+
+    def cloud(n, shift):
+        p = rng.uniform(0, 1, (n, 3)).astype(np.float32) + np.float32(shift)
+        f = rng.uniform(0, 255, (n, 5)).astype(np.float32)
+        return p, f
+
+    c = cvo_mod.Cvo(tum_calib, api=oracle_plain)
+    api, h = c.api, c.h
+    assert c.match_odometry(np.zeros((64, 64, 3), np.uint8), np.zeros((64, 64), np.uint16)) is None  # not init
+    api.set_cloud(h, 0, *cloud(40, 0))
+    api.set_cloud(h, 1, *cloud(41, 0))
+    c.init = True
+    assert c.get_fixed_and_moving_number() == (40, 41)
+    c.update_fixed_pcd()                          # fixed <- moving, moving empty
+    assert c.get_fixed_and_moving_number() == (41, -1)
+    api.set_cloud(h, 1, *cloud(42, 0))
+    # reset_keyframe before any update_previous_pcd: fixed <- moving (cvo.cpp:593-596)
+    odo = np.eye(4, dtype=np.float32)
+    odo[:3, 3] = [0.1, 0.0, 0.0]
+    c.reset_keyframe(odo)
+    assert c.get_fixed_and_moving_number() == (42, -1)
+    assert np.array_equal(c.transform, odo)
+    api.set_cloud(h, 1, *cloud(43, 0))
+    c.update_previous_pcd()                       # previous <- moving
+    assert api.slot_size(h, 2) == 43 and c.pre_pc_init
+    api.set_cloud(h, 1, *cloud(44, 0))
+    c.reset_keyframe(odo)                         # fixed <- previous, previous <- moving
+    assert c.get_fixed_and_moving_number() == (43, -1) and api.slot_size(h, 2) == 44
+    # reset_initial: R,T = inv(transform * odom); returns its inverse (cvo.cpp:611-618)
+    c.transform = odo.copy()
+    back = c.reset_initial(odo)
+    R, T = api.get_RT(h)
+    M = np.eye(4, dtype=np.float32)
+    M[:3, :3], M[:3, 3] = R, T
+    assert np.allclose(M, np.linalg.inv(odo @ odo), atol=1e-6)
+    assert np.allclose(back, odo @ odo, atol=1e-6)
+    c.close()
+
+
+def test_track_sequence_on_oracle(oracle_api, tum_calib):
+    """The LocalTracker call pattern (two cvo objects, persistent R/T/ell) recovers a smooth
+    synthetic trajectory: keyframe tracking of frame k vs frame 0."""
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    scene = synth.make_scene(2)
+    poses = synth.trajectory(5, 2)
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=20 + k))
+              for k, P in enumerate(poses)]
+    out = cvo_mod.track_sequence(frames, tum_calib, api=oracle_api)
+    assert len(out) == 4
+    for k, o in enumerate(out):
+        gt_odo = synth.relative_transform(poses[k], poses[k + 1])
+        gt_kf = synth.relative_transform(poses[0], poses[k + 1])
+        ang, dist = pose_error(o["odometry"], gt_odo)
+        assert ang < 6e-3 and dist < 6e-3, ("odometry", k, ang, dist)
+        ang, dist = pose_error(o["keyframe"], gt_kf)
+        assert ang < 8e-3 and dist < 8e-3, ("keyframe", k, ang, dist)
+        assert 0 < o["r_odometry"]["cos_angle"] <= 1.01
