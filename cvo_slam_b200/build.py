@@ -8,17 +8,19 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcvo_b200.so")
-SOURCES = ["select.cu", "align.cu", "capi.cu"]
+# align.cu is compiled with -fmad=false: every float/double operation of the alignment loop must
+# round exactly as the oracle's (no FMA contraction); its hot loops use explicit _rn intrinsics.
+SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": []}
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "cvo_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in list(SOURCES) + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -26,13 +28,26 @@ def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
     env = dict(os.environ)
     env.pop("CXX", None)   # the image exports a wrapper compiler; let nvcc use the system g++
     env.pop("CC", None)
-    subprocess.check_call(cmd, env=env)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src, flags in SOURCES.items():
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + flags + list(extra) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, env=env)))
+        objs.append(obj)
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    if verbose:
+        print(" ".join(link))
+    subprocess.check_call(link, env=env)
     return OUT
 
 

@@ -4,7 +4,7 @@
 shared library is missing: there is no CPU fallback in the product path.
 
 `LowLevel` is written against a symbol prefix so that the test-only CPU oracle
-(oracle/oracle.py, prefix ``oracle_``) can be driven through the very same Python
+(prefix ``oracle_``, loaded only by the tests) can be driven through the very same Python
 surface; the product never imports the oracle.
 """
 from __future__ import annotations
@@ -48,7 +48,8 @@ class Params(C.Structure):
                 ("max_iter", C.c_int32), ("min_step", C.c_float), ("max_step", C.c_float),
                 ("eps", C.c_float), ("eps_2", C.c_float), ("ell_after_k2", C.c_float),
                 ("ell_after_k9", C.c_float), ("ell_after_k19", C.c_float),
-                ("num_want", C.c_int32), ("feature_type", C.c_int32), ("gray_mode", C.c_int32)]
+                ("num_want", C.c_int32), ("feature_type", C.c_int32), ("gray_mode", C.c_int32),
+                ("exp_mode", C.c_int32)]
 
 
 class AlignResult(C.Structure):

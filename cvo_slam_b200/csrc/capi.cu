@@ -162,6 +162,7 @@ void cvo_default_params(cvo_params *p) {
     p->num_want = 3000;       // pcd_generator.cpp:22
     p->feature_type = 1;      // cvo.cpp:355,366
     p->gray_mode = 0;
+    p->exp_mode = 0;
 }
 
 const char *cvo_last_error(void) { return g_err; }
@@ -374,10 +375,10 @@ int cvo_iteration_at(cvo_handle *h, const float R[9], const float T[3], float el
 
 int cvo_last_pattern(cvo_handle *h, int32_t *ij, float *a, int cap, int *n) {
     if (!h || !h->aws || !n) return CVO_ERR_INVALID;
-    int nm = 0;
-    int rc = cvo_slot_size(h, CVO_SLOT_MOVING, &nm);
+    int nf = 0;
+    int rc = cvo_slot_size(h, CVO_SLOT_FIXED, &nf);
     if (rc != CVO_OK) return rc;
-    return align_last_pattern(h->aws, nm, ij, a, cap, n, h->stream);
+    return align_last_pattern(h->aws, nf, ij, a, cap, n, h->stream);
 }
 
 static int handle_query(cvo_handle *h, int slot_a, const float *Ta, int slot_b, int kind, QueryOut *res) {

@@ -62,6 +62,8 @@ typedef struct cvo_params {
     int32_t num_want;    /* 3000   pcd_generator.cpp:22                            */
     int32_t feature_type;/* 1      cvo.cpp:355,366 (0 = HSV+grad normalised)      */
     int32_t gray_mode;   /* 0 = OpenCV>=4 15-bit RGB2GRAY, 1 = OpenCV 3.x 14-bit  */
+    int32_t exp_mode;    /* 0 = k, ck as the reference: exp in double rounded to float
+                            (cvo.cpp:172-173; bit-faithful trajectory), 1 = MUFU ex2 (fast) */
 } cvo_params;
 
 /* What align() leaves behind (cvo.cpp:763-821) */

@@ -415,6 +415,32 @@ void create_pointcloud(const uint8_t *bgr, size_t bgr_stride, const uint16_t *de
 }
 
 // ---------------------------------------------------------------------------------------------
+// Order-independent summation.  The reference forms each row's flow contribution as an Eigen
+// float dot product `(1/c*Ai)*cross_xy` (cvo.cpp:222-223) whose summation order is an
+// implementation detail of Eigen's vectorised redux, and adds the row results into a double
+// under a spin lock in scheduling order (cvo.cpp:226-230).  The oracle takes the canonical
+// representative of all those orders: the exact sum, rounded once.  Exact sums are kept in a
+// two-limb fixed-point accumulator (value = hi*2^-36 + lo*2^-84): adding is associative, so the
+// CUDA path can reproduce the same bits with any parallel decomposition.
+// ---------------------------------------------------------------------------------------------
+struct ExactAcc {
+    long long hi = 0, lo = 0;
+    inline void add(double t) {
+        double h = std::nearbyint(t * 0x1p36);
+        double r = t - h * 0x1p-36;          // exact
+        hi += (long long)h;
+        lo += (long long)std::nearbyint(r * 0x1p84);
+    }
+    inline void add(const ExactAcc &o) { hi += o.hi; lo += o.lo; }
+    inline double value() const { return (double)hi * 0x1p-36 + (double)lo * 0x1p-84; }
+};
+
+// sin/cos of a float argument, correctly rounded to float (the reference calls std::sin(float)
+// of whatever libm it links, LieGroup.cpp:174-175; the correctly rounded value is the canonical one)
+inline float sin_cr(float x) { return (float)std::sin((double)x); }
+inline float cos_cr(float x) { return (float)std::cos((double)x); }
+
+// ---------------------------------------------------------------------------------------------
 // small float 3x3 helpers (Eigen coefficient-wise products: ((a0*b0 + a1*b1) + a2*b2))
 // ---------------------------------------------------------------------------------------------
 struct M3 { float m[3][3]; };
@@ -467,8 +493,8 @@ void Exp_SEK3(const V3 &w, const V3 &v, float dt, M3 &R, V3 &dT) {
     } else {
         M3 A = skew(w);
         float theta2 = theta * theta;
-        float stheta = std::sin(dt * theta);
-        float ctheta = std::cos(dt * theta);
+        float stheta = sin_cr(dt * theta);
+        float ctheta = cos_cr(dt * theta);
         float oneMinusCosTheta2 = (1 - ctheta) / (theta2);
         M3 A2 = m3_mul(A, A);
         R = m3_add(m3_add(I, m3_scale(A, stheta / theta)), m3_scale(A2, oneMinusCosTheta2));
@@ -816,14 +842,15 @@ struct OracleCvo {
     void compute_flow() {
         se_kernel(ell, prm.sigma * prm.sigma);
         const Cloud &fx = slot[CVO_SLOT_FIXED];
-        double dw[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
         float inv_c = 1 / prm.c, inv_d = 1 / prm.d;
+        ExactAcc tw[3], tv[3];
 #pragma omp parallel
         {
-            double lw[3] = {0, 0, 0}, lv[3] = {0, 0, 0};
+            ExactAcc lw[3], lv[3];
 #pragma omp for schedule(static) nowait
             for (int i = 0; i < fx.n; i++) {
-                float pw[3] = {0, 0, 0}, pv[3] = {0, 0, 0};
+                if (row_ptr[i] == row_ptr[i + 1]) continue;   // an empty row contributes exact zeros
+                ExactAcc rw[3], rv[3];
                 for (int t = row_ptr[i]; t < row_ptr[i + 1]; t++) {
                     const V3 &x = fx.pos[i];
                     const V3 &y = cloud_y[trips[t].j];
@@ -831,17 +858,23 @@ struct OracleCvo {
                     float wa = inv_c * trips[t].a;  // (1/c*Ai)
                     float va = inv_d * trips[t].a;
                     for (int k = 0; k < 3; k++) {
-                        pw[k] = pw[k] + wa * cr[k];
-                        pv[k] = pv[k] + va * (y[k] - x[k]);
+                        float df = y[k] - x[k];
+                        rw[k].add((double)wa * (double)cr[k]);   // products of two floats: exact in double
+                        rv[k].add((double)va * (double)df);
                     }
                 }
-                for (int k = 0; k < 3; k++) { lw[k] += (double)pw[k]; lv[k] += (double)pv[k]; }
+                for (int k = 0; k < 3; k++) {
+                    float pw = (float)rw[k].value();   // the row's float dot product, .cast<double>()
+                    float pv = (float)rv[k].value();
+                    lw[k].add((double)pw);
+                    lv[k].add((double)pv);
+                }
             }
 #pragma omp critical
-            for (int k = 0; k < 3; k++) { dw[k] += lw[k]; dv[k] += lv[k]; }
+            for (int k = 0; k < 3; k++) { tw[k].add(lw[k]); tv[k].add(lv[k]); }
         }
         A_nonzero = (int)trips.size();
-        for (int k = 0; k < 3; k++) { omega[k] = (float)dw[k]; v[k] = (float)dv[k]; }
+        for (int k = 0; k < 3; k++) { omega[k] = (float)tw[k].value(); v[k] = (float)tv[k].value(); }
     }
 
     // cvo.cpp:239-334
@@ -872,8 +905,10 @@ struct OracleCvo {
         float m2tc = (float)(-2.0 * temp_coef);
         float p2tc = (float)(2.0 * temp_coef);
         float mtc = -temp_coef;
-        double B = 0, C = 0, D = 0, E = 0;
-#pragma omp parallel for schedule(static) reduction(+ : B, C, D, E)
+        // per-row sums (cvo.cpp:277-306), then rows added in ascending order: the reference adds them
+        // under a spin lock in scheduling order; a fixed order keeps the oracle machine-independent
+        std::vector<double> rB(fx.n, 0.0), rC(fx.n, 0.0), rD(fx.n, 0.0), rE(fx.n, 0.0);
+#pragma omp parallel for schedule(static)
         for (int i = 0; i < fx.n; i++) {  // :275-315
             double Bi = 0, Ci = 0, Di = 0, Ei = 0;
             for (int t = row_ptr[i]; t < row_ptr[i + 1]; t++) {
@@ -895,8 +930,10 @@ struct OracleCvo {
                 Ei += double(A_ij * (epsil_ij + beta_ij * delta_ij + 1 / 2.0 * beta_ij * beta_ij * gamma_ij +
                                      1 / 2.0 * gamma_ij * gamma_ij + 1 / 24.0 * beta_ij * beta_ij * beta_ij * beta_ij));
             }
-            B += Bi; C += Ci; D += Di; E += Ei;
+            rB[i] = Bi; rC[i] = Ci; rD[i] = Di; rE[i] = Ei;
         }
+        double B = 0, C = 0, D = 0, E = 0;
+        for (int i = 0; i < fx.n; i++) { B += rB[i]; C += rC[i]; D += rD[i]; E += rE[i]; }
         cB = B; cC = C; cD = D; cE = E;
         // :317-333
         float p0 = 4.0 * float(E), p1 = 3.0 * float(D), p2 = 2.0 * float(C), p3 = float(B);
@@ -1170,7 +1207,7 @@ void oracle_default_params(cvo_params *p) {
     p->c_ell = 200.f; p->c_sigma = 1.f; p->max_iter = 2000; p->min_step = 2 * 1.0e-1f;
     p->max_step = 0.8f; p->eps = 5 * 1.0e-5f; p->eps_2 = 1.0e-5f;
     p->ell_after_k2 = 0.10f; p->ell_after_k9 = 0.06f; p->ell_after_k19 = 0.03f;
-    p->num_want = 3000; p->feature_type = 1; p->gray_mode = 0;
+    p->num_want = 3000; p->feature_type = 1; p->gray_mode = 0; p->exp_mode = 0;
 }
 
 int oracle_create(const cvo_calib *c, const cvo_params *p, oracle_handle **out) {

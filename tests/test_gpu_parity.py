@@ -2,9 +2,14 @@
 
 Bars (BASELINE.json north_star / SURVEY §8d "Parity gates"):
   * point selection, pixel coordinates, positions, features: bit-exact
-  * in-cutoff pattern at an injected (R, T, ell): identical except ties |a - sp|/sp < 1e-5
-  * omega, v: 1e-5 relative; B..E, step: 1e-4 relative (fp32 terms, fp64 sums)
-  * final pose after the same schedule: 1e-4 rad / 1e-4 m
+  * default (exact) mode, injected (R, T, ell): identical in-cutoff pattern, a_ij, omega, v to the
+    bit; B..E to 1e-12 relative (double sums in a different order); step to 1e-6
+  * default mode, free running: same iteration count as the oracle, final pose within
+    1e-4 rad / 1e-4 m (observed ~1e-7)
+  * fast mode (exp_mode = 1, MUFU ex2): pattern identical except ties |a - sp|/sp < 1e-5,
+    a_ij to 3e-6, omega / v to 1e-5, B..E and step to 1e-4; the free-running trajectory
+    decorrelates from the oracle's in the chaotic tail, so its final pose is
+    only required to sit in the same basin
   * inner products: 1e-4 relative; Hessian: 1e-4 of its largest entry
 """
 import numpy as np
@@ -121,7 +126,7 @@ def _pattern_keys(ij):
     return ij[:, 0].astype(np.int64) * (1 << 20) + ij[:, 1].astype(np.int64)
 
 
-def _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, sp=8e-3):
+def _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, sp=8e-3, exact=True):
     rc = cuda_api.iteration_at(hc, R, T, ell)
     ro = oracle_api.iteration_at(ho, R, T, ell)
     ijc, ac, nc = cuda_api.last_pattern(hc, 1 << 20)
@@ -130,6 +135,16 @@ def _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, sp=8e-3):
     kc, ko = _pattern_keys(ijc), _pattern_keys(ijo)
     oc, oo = np.argsort(kc), np.argsort(ko)
     kc, ac, ko, ao = kc[oc], ac[oc], ko[oo], ao[oo]
+    if exact:
+        assert np.array_equal(kc, ko), "in-cutoff pattern differs"
+        assert np.array_equal(ac.view(np.uint32), ao.view(np.uint32)), \
+            f"{int((ac != ao).sum())} of {len(ao)} kernel values differ in the last bits"
+        assert np.array_equal(rc["omega"].view(np.uint32), ro["omega"].view(np.uint32))
+        assert np.array_equal(rc["v"].view(np.uint32), ro["v"].view(np.uint32))
+        for key in "BCDE":
+            assert rc[key] == pytest.approx(ro[key], rel=1e-12, abs=1e-300), key
+        assert rc["step"] == pytest.approx(ro["step"], rel=1e-6)
+        return 0, no
     only_c = np.setdiff1d(kc, ko, assume_unique=True)
     only_o = np.setdiff1d(ko, kc, assume_unique=True)
     # documented cutoff ties: MUFU ex2 vs double exp can flip `a > sp_thres` within 1e-5 relative
@@ -153,32 +168,42 @@ def _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, sp=8e-3):
     return ties, no
 
 
-def test_iteration_parity_golden(cuda_api, oracle_api, golden_small):
+def _injected_states(g):
+    from cvo_slam_b200 import synth
+    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    states = [(I, z, ell) for ell in (0.15, 0.10, 0.06, 0.03)]
+    Tf = g["align_transform"].astype(np.float64)
+    rng = np.random.default_rng(0)
+    for k in range(4):   # near the solution: inverse of the oracle's final transform, perturbed
+        P = synth.pose(rng.normal(0, 2e-3, 3), rng.normal(0, 2e-3, 3))
+        M = np.linalg.inv(Tf @ P)
+        states.append((M[:3, :3].astype(np.float32), M[:3, 3].astype(np.float32), (0.10, 0.06, 0.03, 0.03)[k]))
+    return states
+
+
+@pytest.mark.parametrize("exp_mode", [0, 1])
+def test_iteration_parity_golden(cuda_api, oracle_api, golden_small, exp_mode):
     g = golden_small
-    hc, ho = _both(cuda_api, oracle_api, _calib_of(g))
+    p = cuda_api.default_params()
+    p.exp_mode = exp_mode
+    hc, ho = cuda_api.create(_calib_of(g), p), oracle_api.create(_calib_of(g))
     for api, h in ((cuda_api, hc), (oracle_api, ho)):
         api.set_cloud(h, 0, g["pos_a"], g["feat_a"])
         api.set_cloud(h, 1, g["pos_b"], g["feat_b"])
-    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
     total_ties = 0
-    for ell in (0.15, 0.10, 0.06, 0.03):
-        ties, n = _check_iteration(cuda_api, oracle_api, hc, ho, I, z, ell)
+    for R, T, ell in _injected_states(g):
+        ties, n = _check_iteration(cuda_api, oracle_api, hc, ho, R, T, ell, exact=(exp_mode == 0))
         total_ties += ties
-    # states near the solution: (R, T) = inverse of the oracle's final transform, perturbed
-    Tf = g["align_transform"].astype(np.float64)
-    rng = np.random.default_rng(0)
-    for k in range(4):
-        from cvo_slam_b200 import synth
-        P = synth.pose(rng.normal(0, 2e-3, 3), rng.normal(0, 2e-3, 3))
-        M = np.linalg.inv(Tf @ P)
-        ties, n = _check_iteration(cuda_api, oracle_api, hc, ho, M[:3, :3].astype(np.float32),
-                                   M[:3, 3].astype(np.float32), (0.10, 0.06, 0.03, 0.03)[k])
-        total_ties += ties
-    # golden vectors (made with the reference's nanoflann): nnz at the identity state
+    # golden vectors (made with the reference's nanoflann) at the identity state
+    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
     rec = cuda_api.iteration_at(hc, I, z, 0.15)
-    assert abs(rec["nnz"] - int(g["it0_nnz"])) <= 2
-    assert np.allclose(rec["omega"], g["it0_omega"], rtol=1e-5, atol=1e-5 * np.abs(g["it0_omega"]).max())
-    print("cutoff ties over 8 injected states:", total_ties)
+    if exp_mode == 0:
+        assert rec["nnz"] == int(g["it0_nnz"])
+        assert np.array_equal(rec["omega"], g["it0_omega"]) and np.array_equal(rec["v"], g["it0_v"])
+    else:
+        assert abs(rec["nnz"] - int(g["it0_nnz"])) <= 2
+        assert np.allclose(rec["omega"], g["it0_omega"], rtol=1e-5, atol=1e-5 * np.abs(g["it0_omega"]).max())
+    print("exp_mode", exp_mode, "cutoff ties over 8 injected states:", total_ties)
     cuda_api.destroy(hc)
     oracle_api.destroy(ho)
 
@@ -194,23 +219,20 @@ def test_align_parity_golden(cuda_api, golden_small):
     assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
     assert res.status == 0
     assert res.ell == pytest.approx(float(g["align_ell"]))
-    assert abs(res.iterations - int(g["align_scalars"][0])) <= 10     # reported, loosely bounded
-    n = min(len(recs), len(g["trace_nnz"]), 21)
-    assert np.array_equal([r["ell"] for r in recs[:n]], g["trace_ell"][:n])
-    # early iterations follow the oracle's trajectory closely
-    for k in range(4):
-        assert np.allclose(recs[k]["omega"], g["trace_omega"][k], rtol=1e-3, atol=1e-4)
-        assert abs(recs[k]["nnz"] - g["trace_nnz"][k]) <= max(3, g["trace_nnz"][k] // 1000)
+    assert [res.iterations, res.iter, res.A_nonzero] == g["align_scalars"].tolist()
+    n = len(recs)
+    assert np.array_equal([r["ell"] for r in recs], g["trace_ell"][:n])
+    # the whole trajectory follows the golden trace
+    assert np.array_equal([r["nnz"] for r in recs], g["trace_nnz"][:n])
+    assert np.allclose(np.array([r["omega"] for r in recs]), g["trace_omega"][:n], rtol=1e-5, atol=1e-9)
+    assert np.allclose(np.array([r["step"] for r in recs]), g["trace_step"][:n], rtol=1e-5)
     # queries at the final state
     T = res.transform_np()
     vals = [cuda_api.inner_product(h, 1, None, 0), cuda_api.inner_product(h, 1, T, 0),
             cuda_api.inner_product(h, 0, None, 0), cuda_api.inner_product(h, 1, None, 1)]
     for (v, n_), gv, gn, name in zip(vals, g["inner_values"], g["inner_nums"], ("pre", "post", "fixed", "moving")):
-        if name == "post":     # evaluated at slightly different final poses
-            assert v == pytest.approx(float(gv), rel=5e-3)
-        else:
-            assert v == pytest.approx(float(gv), rel=INNER_RTOL), name
-            assert n_ == int(gn), name
+        assert v == pytest.approx(float(gv), rel=INNER_RTOL), name
+        assert n_ == int(gn), name
     cuda_api.destroy(h)
 
 
@@ -250,6 +272,7 @@ def test_align_parity_c1(cuda_api, oracle_api, tum_calib, pair_c1):
     ang, dist = pose_error(rc.transform_np(), ro.transform_np())
     print("C1: iterations gpu/oracle", rc.iterations, ro.iterations, "pose diff", ang, dist)
     assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    assert rc.iterations == ro.iterations and rc.A_nonzero == ro.A_nonzero
     ang, dist = pose_error(rc.transform_np(), T_gt)
     assert ang < 5e-3 and dist < 5e-3
     # state persists: a second align of the same object starts from R, T, ell left behind
@@ -260,8 +283,32 @@ def test_align_parity_c1(cuda_api, oracle_api, tum_calib, pair_c1):
     ro2, _ = oracle_api.align(ho)
     ang, dist = pose_error(rc2.transform_np(), ro2.transform_np())
     assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    assert rc2.iterations == ro2.iterations
     cuda_api.destroy(hc)
     oracle_api.destroy(ho)
+
+
+def test_align_fast_mode_same_basin(cuda_api, oracle_api, tum_calib, pair_c1):
+    """exp_mode = 1 (MUFU ex2): same schedule for the first 10 iterations within 1e-4; free running
+    it ends in the same basin as the oracle (the tail is chaotic)."""
+    bgr_a, d_a, bgr_b, d_b, T_gt = pair_c1
+    for max_iter, tol in ((10, 1e-4), (2000, 2e-3)):
+        p = cuda_api.default_params()
+        p.exp_mode = 1
+        p.max_iter = max_iter
+        q = oracle_api.default_params()
+        q.max_iter = max_iter
+        hc, ho = cuda_api.create(tum_calib, p), oracle_api.create(tum_calib, q)
+        for api, h in ((cuda_api, hc), (oracle_api, ho)):
+            api.set_frame(h, 0, bgr_a, d_a)
+            api.set_frame(h, 1, bgr_b, d_b)
+        rc, _ = cuda_api.align(hc)
+        ro, _ = oracle_api.align(ho)
+        ang, dist = pose_error(rc.transform_np(), ro.transform_np())
+        print("fast mode max_iter", max_iter, "iterations", rc.iterations, ro.iterations, "pose diff", ang, dist)
+        assert ang < tol and dist < tol
+        cuda_api.destroy(hc)
+        oracle_api.destroy(ho)
 
 
 def test_align_eth3d_large_ell(cuda_api, oracle_api):
@@ -283,6 +330,7 @@ def test_align_eth3d_large_ell(cuda_api, oracle_api):
         ang, dist = pose_error(rc.transform_np(), ro.transform_np())
         print("C4 ell", ell, "iterations", rc.iterations, ro.iterations, "pose diff", ang, dist)
         assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+        assert rc.iterations == ro.iterations
         cuda_api.destroy(hc)
         oracle_api.destroy(ho)
 
@@ -349,7 +397,8 @@ def test_batch_matches_single_and_oracle(cuda_api, oracle_api, tum_calib):
         ang, dist = pose_error(r["transform"].reshape(4, 4), gt)
         assert ang < 6e-3 and dist < 6e-3
         vo, _ = oracle_api.inner_product(ho, 1, ro.transform_np(), 0)
-        assert v == pytest.approx(vo, rel=5e-3)
+        assert v == pytest.approx(vo, rel=INNER_RTOL)
+        assert r["iterations"] == ro.iterations
         oracle_api.destroy(ho)
     # the batch path and the handle path run the same kernel: identical bits
     hc = cuda_api.create(tum_calib)
@@ -379,7 +428,7 @@ def test_tracking_sequence_parity(cuda_api, oracle_api, tum_calib):
             assert ang < POSE_TOL_RAD and dist < POSE_TOL_M, (k, key, ang, dist)
         for key in ("inn_pre", "inn_fixed_pcd", "inn_moving_pcd"):
             assert c["r_odometry"][key].value == pytest.approx(o["r_odometry"][key].value, rel=INNER_RTOL)
-        assert c["r_odometry"]["inn_post"].value == pytest.approx(o["r_odometry"]["inn_post"].value, rel=5e-3)
-        assert c["r_odometry"]["cos_angle"] == pytest.approx(o["r_odometry"]["cos_angle"], rel=5e-3)
+        assert c["r_odometry"]["inn_post"].value == pytest.approx(o["r_odometry"]["inn_post"].value, rel=INNER_RTOL)
+        assert c["r_odometry"]["cos_angle"] == pytest.approx(o["r_odometry"]["cos_angle"], rel=INNER_RTOL)
         Hc, Ho = c["r_odometry"]["post_hessian"], o["r_odometry"]["post_hessian"]
-        assert np.allclose(Hc, Ho, rtol=0, atol=2e-2 * np.abs(Ho).max())
+        assert np.allclose(Hc, Ho, rtol=0, atol=1e-4 * np.abs(Ho).max())
