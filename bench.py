@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — CVO frame-pair alignments/s on synthetic 640x480 RGB-D keyframe pairs.
+
+Workload (BASELINE.json configs[4], the configuration the multi-GPU metric is quoted on; it is
+the largest single-GPU configuration and the one that shards): F keyframes of one synthetic
+scene (TUM fr1 intrinsics), P = 8 F independent keyframe pairs with a perturbed prior
+(`reset_initial`), as in loop-closure verification (src/keyframe_graph.cpp:622-731).
+One *step* = point selection + features for all F frames, alignment of all P pairs, and the
+post-alignment inner product <T*moving, fixed> of every pair.  Weak scaling: every rank
+processes its own F frames / P pairs; `value` = pairs of all ranks / max-over-ranks step time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA path (libcvo_b200.so)
+  python bench.py --impl reference ...                           # CPU reference arm (oracle)
+
+`value`: inputs resident in HBM when the timed region starts, timed with CUDA events on the
+stream the kernels run on.  `e2e`: the same step through the C ABI with HOST (pinned) images,
+H2D of every frame and D2H of every result inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+PARTNER_OFFSETS = [1, 2, 3, 5, 8, 13, 21, 34]
+FLOP_PER_EVAL = 28          # d2 8 + d2c 14 + 2 scales + products/compare 4
+FLOP_PER_NNZ_ITER = 90      # flow 24 + step-size ~66 (cvo.cpp:213-223, 282-306)
+SM_COUNT, FP32_LANES, MUFU_LANES = 148, 128, 16
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cvo_b200", choices=["cvo_b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1024, help="keyframes per GPU")
+    ap.add_argument("--partners", type=int, default=8, help="pairs per keyframe")
+    ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded CPU sample")
+    ap.add_argument("--exp-mode", type=int, default=0, help="0 exact (bit-faithful), 1 MUFU fast")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---- workload ------------------------------------------------------------------------------------
+def keyframe_poses(n, seed):
+    from cvo_slam_b200 import synth
+    rng = np.random.default_rng(seed)
+    return [synth.pose(rng.uniform(-0.035, 0.035, 3), rng.uniform(-0.05, 0.05, 3)) for _ in range(n)]
+
+
+def pair_list(n_frames, partners):
+    offs = PARTNER_OFFSETS[:partners]
+    return [(i, (i + o) % n_frames) for i in range(n_frames) for o in offs]
+
+
+def pair_priors(pairs, poses, seed):
+    """initial (R, T) per pair: the inverse of a perturbed ground-truth transform, i.e. what
+    reset_initial (cvo.cpp:611-618) leaves in R, T from a PnP prior."""
+    from cvo_slam_b200 import synth
+    rng = np.random.default_rng(seed)
+    R = np.zeros((len(pairs), 9), np.float32)
+    T = np.zeros((len(pairs), 3), np.float32)
+    gts = []
+    for k, (fi, mi) in enumerate(pairs):
+        gt = synth.relative_transform(poses[fi], poses[mi])
+        prior = gt @ synth.pose(rng.normal(0, 0.004, 3), rng.normal(0, 0.006, 3))
+        M = np.linalg.inv(prior)
+        R[k] = M[:3, :3].astype(np.float32).reshape(9)
+        T[k] = M[:3, 3].astype(np.float32)
+        gts.append(gt)
+    return R, T, gts
+
+
+def render_frames(frame_ids, poses, seed, device):
+    """-> (bgr uint8 [n,H,W,3], depth uint16 [n,H,W]) torch tensors on `device`."""
+    import torch
+    from cvo_slam_b200 import capi, synth
+    cal = capi.TUM1_CALIB()
+    scene = synth.make_scene(seed)
+    bgr = torch.empty((len(frame_ids), H, W, 3), dtype=torch.uint8, device=device)
+    dep = torch.empty((len(frame_ids), H, W), dtype=torch.int16, device=device)   # uint16 bit pattern
+    for k, f in enumerate(frame_ids):
+        b, d = synth.render(scene, poses[f], cal, W, H, noise_seed=seed * 100003 + f, device=device)
+        bgr[k] = b
+        dep[k] = d.view(torch.int16)
+    return bgr, dep
+
+
+# ---- clocks --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---- CPU reference (oracle) leg --------------------------------------------------------------------
+def cpu_leg(pairs, poses, R0, T0, seed, n_pairs, steps, warmup, device):
+    """Times the CPU restatement of the reference (all host threads) on a bounded sample: the first
+    `n_pairs` pairs of the same workload; returns alignments/s and a description."""
+    from cvo_slam_b200 import capi
+    from oracle import oracle
+    orc = oracle.load()
+    cal = capi.TUM1_CALIB()
+    sample = pairs[:n_pairs]
+    frame_ids = sorted({f for p in sample for f in p})
+    bgr, dep = render_frames(frame_ids, poses, seed, device)
+    bgr, dep = bgr.cpu().numpy(), dep.cpu().numpy().view(np.uint16)
+    local = {f: k for k, f in enumerate(frame_ids)}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        # one cvo object per frame provides set_pcd once per frame; pairs reuse the clouds
+        clouds = {}
+        h = orc.create(cal)
+        for f in frame_ids:
+            orc.set_frame(h, 0, bgr[local[f]], dep[local[f]])
+            clouds[f] = orc.get_cloud(h, 0)
+        for k, (fi, mi) in enumerate(sample):
+            orc.set_cloud(h, 0, *clouds[fi])
+            orc.set_cloud(h, 1, *clouds[mi])
+            orc.set_ell(h, 0.15)
+            orc.set_RT(h, R0[k].reshape(3, 3), T0[k])
+            res, _ = orc.align(h)
+            orc.inner_product(h, 1, res.transform_np(), 0)
+        orc.destroy(h)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_step = sum(times) / len(times)
+    return dict(value=len(sample) / per_step, unit="alignments/s", cores=orc.num_threads(),
+                kind="port",
+                sample=f"{len(sample)} pairs over {len(frame_ids)} keyframes of the same workload, "
+                       f"{steps} timed repetitions; oracle/{'_ref nanoflann KD-tree' if orc.has_nanoflann else 'cell-list'} "
+                       f"radius search, OpenMP over points"), per_step * 1e3
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_frames, n_pairs = a.frames, a.frames * a.partners
+    seed = 1000 + rank
+    poses = keyframe_poses(n_frames, seed)
+    pairs = pair_list(n_frames, a.partners)
+    R0, T0, gts = pair_priors(pairs, poses, seed)
+    config = dict(workload=f"C5 batch: {n_frames} synthetic 640x480 keyframes x {a.partners} partners = {n_pairs} "
+                           f"independent pairs per GPU (loop-closure verification shape), TUM fr1 intrinsics, "
+                           f"prior via reset_initial; step = select {n_frames} frames + align {n_pairs} pairs + inner products",
+                  frames_per_gpu=n_frames, pairs_per_gpu=n_pairs, exp_mode=a.exp_mode,
+                  l2="inputs per step (%.0f MB) exceed the 126 MB L2" % (n_frames * W * H * 5 / 1e6))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        cb, ms = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, a.steps, a.warmup, dev)
+        line = dict(metric="cvo_frame_pair_alignments_per_s", value=cb["value"], unit="alignments/s", n_gpus=a.gpus,
+                    steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32 (f64 exp)", data="synthetic", config=config, impl="reference",
+                    cpu_baseline=cb,
+                    e2e=dict(value=cb["value"], unit="alignments/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cvo_slam_b200 import batch as B, capi
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    api = capi.load()
+    cal = capi.TUM1_CALIB()
+    prm = api.default_params()
+    prm.exp_mode = a.exp_mode
+
+    bgr_d, dep_d = render_frames(list(range(n_frames)), poses, seed, dev)
+    torch.cuda.synchronize()
+    bt = B.Batch(cal, prm, max_frames=n_frames, max_pairs=n_pairs, width=W, height=H, device=local_rank, api=api)
+    desc = bt.make_pairs(pairs, R0.reshape(-1, 3, 3), T0, prm.ell_init)
+
+    def step_device():
+        bt.mark(0)
+        bt.set_frames_ptr(bgr_d.data_ptr(), dep_d.data_ptr(), n_frames, device=True)
+        res = bt.align(desc)
+        vals, nums = bt.inner_product(desc, res)
+        bt.mark(1)
+        return res, vals, bt.elapsed_ms(), bt.last_align_ms()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        res, vals, _, _ = step_device()
+    s0 = bt.stats()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_dev, t_align = 0.0, 0.0
+    wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        res, vals, ms, ams = step_device()
+        t_dev += ms
+        t_align += ams
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    s1 = bt.stats()
+
+    # ---- end to end: host (pinned) images through the C ABI ------------------------------------------
+    bgr_h = torch.empty(bgr_d.shape, dtype=torch.uint8, pin_memory=True).copy_(bgr_d)
+    dep_h = torch.empty(dep_d.shape, dtype=torch.int16, pin_memory=True).copy_(dep_d)
+    torch.cuda.synchronize()
+
+    def step_host():
+        bt.set_frames_ptr(bgr_h.data_ptr(), dep_h.data_ptr(), n_frames, device=False)
+        r = bt.align(desc)
+        v, n = bt.inner_product(desc, r)
+        return r, v
+
+    for _ in range(min(a.warmup, 2)):
+        step_host()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(a.steps):
+        res_h, vals_h = step_host()
+    barrier()
+    e2e_s = (time.perf_counter() - e0) / a.steps
+
+    # sanity inside the bench: results of the two legs agree, alignments converged to the truth
+    assert np.array_equal(res_h["transform"], res["transform"])
+    err = []
+    for k in range(0, n_pairs, max(1, n_pairs // 64)):
+        E = np.linalg.inv(gts[k]) @ res["transform"][k].reshape(4, 4).astype(np.float64)
+        err.append(np.linalg.norm(E[:3, 3]))
+    status_bad = int((res["status"] != 0).sum())
+
+    ms_step = t_dev / a.steps
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_pairs = n_pairs * world
+    value = total_pairs / (ms_step * 1e-3)
+    evals = (s1["evals"] - s0["evals"]) / a.steps
+    nnz_it = (s1["nnz"] - s0["nnz"]) / a.steps
+    iters = (s1["iterations"] - s0["iterations"]) / a.steps
+    launches = (s1["launches"] - s0["launches"]) // a.steps
+    align_ms = t_align / a.steps
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
+    flops = evals * FLOP_PER_EVAL + nnz_it * FLOP_PER_NNZ_ITER
+    achieved = flops / (align_ms * 1e-3) / 1e12
+    roofline = dict(bound="fp32 (non-tensor; exact mode adds 2 fp64 exp per eval)" if a.exp_mode == 0 else "fp32+mufu",
+                    kernel="k_align_batch", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
+                    frac=achieved / fp32_peak, traffic=None,
+                    peak_source=f"derived: {SM_COUNT} SM x {FP32_LANES} lanes x 2 x observed SM clock {sm_mhz:.0f} MHz "
+                                f"(MEASURED_PEAKS.json has no fp32 figure)",
+                    kernel_ms_per_launch=align_ms, kernel_share_of_step=align_ms / ms_step,
+                    evals_per_launch=evals, evals_per_s=evals / (align_ms * 1e-3),
+                    eval_roofline_per_s=min(fp32_peak * 1e12 / FLOP_PER_EVAL,
+                                            SM_COUNT * MUFU_LANES * sm_mhz * 1e6 / 2),
+                    iterations_per_pair=iters / n_pairs, nnz_per_iteration=nnz_it / max(iters, 1))
+    line = dict(metric="cvo_frame_pair_alignments_per_s", value=value, unit="alignments/s", n_gpus=world,
+                steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32 (f64 exp)" if a.exp_mode == 0 else "f32", data="synthetic",
+                config=config, clocks=clocks,
+                e2e=dict(value=total_pairs / e2e_s, unit="alignments/s",
+                         h2d_bytes_per_step=int(n_frames * W * H * 5 + desc.nbytes * 2),
+                         d2h_bytes_per_step=int(res.nbytes + n_pairs * 192)),
+                gpu_launches=int(launches * a.steps), roofline=roofline,
+                wall_ms_per_step=wall / a.steps * 1e3,
+                check=dict(median_translation_error_m=float(np.median(err)), pairs_with_error_status=status_bad))
+    if world == 1 and not a.no_cpu_baseline:
+        cb, _ = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, 1, 0, dev)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    bt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

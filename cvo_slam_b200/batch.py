@@ -89,9 +89,17 @@ class Batch:
         return vals, nums
 
     def stats(self):
-        s = (C.c_int64 * 3)()
+        s = (C.c_int64 * 4)()
         self.api._check(self.lib.cvo_batch_stats(self.b, s), "batch_stats")
-        return dict(launches=s[0], evals=s[1], iterations=s[2])
+        return dict(launches=s[0], evals=s[1], iterations=s[2], nnz=s[3])
+
+    def mark(self, which):
+        self.api._check(self.lib.cvo_batch_mark(self.b, which), "batch_mark")
+
+    def elapsed_ms(self):
+        ms = C.c_float(0)
+        self.api._check(self.lib.cvo_batch_elapsed_ms(self.b, C.byref(ms)), "batch_elapsed_ms")
+        return ms.value
 
     def last_align_ms(self):
         ms = C.c_float(0)

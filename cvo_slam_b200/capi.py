@@ -309,6 +309,8 @@ class CudaLowLevel(LowLevel):
         lib.cvo_batch_inner_product.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         lib.cvo_batch_stats.argtypes = [vp, P(C.c_int64)]
         lib.cvo_batch_last_align_ms.argtypes = [vp, P(C.c_float)]
+        lib.cvo_batch_mark.argtypes = [vp, C.c_int]
+        lib.cvo_batch_elapsed_ms.argtypes = [vp, P(C.c_float)]
 
     def create(self, calib, params=None, device=0):
         if params is None:
@@ -328,9 +330,9 @@ class CudaLowLevel(LowLevel):
                     "set_frame_device")
 
     def handle_stats(self, h):
-        s = (C.c_int64 * 3)()
+        s = (C.c_int64 * 4)()
         self._check(self.lib.cvo_handle_stats(h, s), "handle_stats")
-        return dict(launches=s[0], evals=s[1], iterations=s[2])
+        return dict(launches=s[0], evals=s[1], iterations=s[2], nnz=s[3])
 
 
 _lib = None

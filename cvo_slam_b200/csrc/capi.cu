@@ -82,7 +82,7 @@ struct cvo_batch {
     int w = 0, h = 0, max_frames = 0, max_pairs = 0, chunk = 0;
     CloudArena arena;
     SelWorkspace *sel[2] = {nullptr, nullptr};
-    cudaEvent_t sel_done[2] = {nullptr, nullptr}, ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t sel_done[2] = {nullptr, nullptr}, ev0 = nullptr, ev1 = nullptr, ev_user[2] = {nullptr, nullptr};
     AlignWorkspace *aws = nullptr;
     AlignTask *d_tasks = nullptr;
     cvo_align_result *d_results = nullptr;
@@ -470,11 +470,11 @@ int cvo_get_selection_debug(cvo_handle *h, int slot, uint8_t *map, int32_t info[
     return sel_debug(h->sel, 0, map, info, h->stream);
 }
 
-int cvo_handle_stats(cvo_handle *h, int64_t stats[3]) {
+int cvo_handle_stats(cvo_handle *h, int64_t stats[4]) {
     if (!h || !stats) return CVO_ERR_INVALID;
     stats[0] = h->launches;
-    stats[1] = h->aws ? align_ws_evals(h->aws, h->stream) : 0;
-    stats[2] = h->aws ? align_ws_iters(h->aws, h->stream) : 0;
+    stats[1] = stats[2] = stats[3] = 0;
+    if (h->aws) align_ws_stats(h->aws, h->stream, stats + 1);
     return CVO_OK;
 }
 
@@ -502,6 +502,8 @@ int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int devic
         for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->sel_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&b->ev_user[0]);
+        if (e == cudaSuccess) e = cudaEventCreate(&b->ev_user[1]);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_tasks, sizeof(AlignTask) * max_pairs);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_results, sizeof(cvo_align_result) * max_pairs);
         if (e == cudaSuccess) e = cudaMalloc(&b->d_q, sizeof(QueryTask) * max_pairs);
@@ -532,6 +534,7 @@ int cvo_batch_destroy(cvo_batch *b) {
     for (int i = 0; i < 2; i++) if (b->sel_done[i]) cudaEventDestroy(b->sel_done[i]);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    for (int i = 0; i < 2; i++) if (b->ev_user[i]) cudaEventDestroy(b->ev_user[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
@@ -641,11 +644,24 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
     return CVO_OK;
 }
 
-int cvo_batch_stats(cvo_batch *b, int64_t stats[3]) {
+int cvo_batch_stats(cvo_batch *b, int64_t stats[4]) {
     if (!b || !stats) return CVO_ERR_INVALID;
     stats[0] = b->launches;
-    stats[1] = align_ws_evals(b->aws, b->stream);
-    stats[2] = align_ws_iters(b->aws, b->stream);
+    align_ws_stats(b->aws, b->stream, stats + 1);
+    return CVO_OK;
+}
+
+int cvo_batch_mark(cvo_batch *b, int which) {
+    if (!b || which < 0 || which > 1) return CVO_ERR_INVALID;
+    CVO_CUDA_TRY(cudaSetDevice(b->device));
+    CVO_CUDA_TRY(cudaEventRecord(b->ev_user[which], b->stream));
+    return CVO_OK;
+}
+
+int cvo_batch_elapsed_ms(cvo_batch *b, float *ms) {
+    if (!b || !ms) return CVO_ERR_INVALID;
+    CVO_CUDA_TRY(cudaEventSynchronize(b->ev_user[1]));
+    CVO_CUDA_TRY(cudaEventElapsedTime(ms, b->ev_user[0], b->ev_user[1]));
     return CVO_OK;
 }
 

@@ -100,8 +100,8 @@ int align_run(AlignWorkspace *ws, const cvo_params &prm, int n_tasks, const Alig
 // debug: in-cutoff pattern left in workgroup 0's scratch by the last run (host arrays)
 int align_last_pattern(AlignWorkspace *ws, int n_fixed, int32_t *ij, float *a, int cap, int *n,
                        cudaStream_t stream);
-int64_t align_ws_evals(AlignWorkspace *ws, cudaStream_t stream);   // cumulative kernel evals
-int64_t align_ws_iters(AlignWorkspace *ws, cudaStream_t stream);
+// cumulative {kernel evals, iterations, sum of nnz over iterations}
+void align_ws_stats(AlignWorkspace *ws, cudaStream_t stream, int64_t out[3]);
 
 struct QueryTask {          // <Ta * a, b> at `ell`
     CloudView a, b;

@@ -177,11 +177,16 @@ int cvo_batch_align(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
 /* per-pair <T*moving, fixed> at each pair's final ell (compute_innerproduct_lc, cvo.cpp:545) */
 int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
                             const cvo_align_result *results, float *values, int *nums);
-/* counters since creation: {kernel launches, in-cutoff kernel evaluations, iterations} */
-int cvo_batch_stats(cvo_batch *b, int64_t stats[3]);
-int cvo_handle_stats(cvo_handle *h, int64_t stats[3]);
+/* counters since creation: {kernel launches, in-cutoff kernel evaluations (d2 < d2_thres),
+ * align iterations, stored non-zeros summed over iterations} */
+int cvo_batch_stats(cvo_batch *b, int64_t stats[4]);
+int cvo_handle_stats(cvo_handle *h, int64_t stats[4]);
 /* device-time of the last cvo_batch_align's kernel in ms (CUDA events on its stream) */
 int cvo_batch_last_align_ms(cvo_batch *b, float *ms);
+/* CUDA events on the batch's own stream (the stream every kernel of the batch is launched on):
+ * mark(0) before and mark(1) after a region, elapsed_ms waits for mark 1 and returns the time. */
+int cvo_batch_mark(cvo_batch *b, int which);
+int cvo_batch_elapsed_ms(cvo_batch *b, float *ms);
 
 #ifdef __cplusplus
 }
