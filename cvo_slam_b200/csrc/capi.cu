@@ -72,6 +72,7 @@ struct cvo_handle {
     char *pinned = nullptr;       // host staging
     int trace_cap = 0;
     int64_t launches = 0;
+    int last_nnz = 0;
 };
 
 struct cvo_batch {
@@ -344,6 +345,7 @@ static int handle_run_align(cvo_handle *h, const float R[9], const float T[3], f
     CVO_CUDA_TRY(cudaMemcpyAsync(hr, h->d_res, sizeof(cvo_align_result), cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (out) *out = *hr;
+    h->last_nnz = hr->A_nonzero;
     if (tc) {
         int n = hr->iterations < tc ? hr->iterations : tc;
         if (n > 0) {
@@ -375,10 +377,7 @@ int cvo_iteration_at(cvo_handle *h, const float R[9], const float T[3], float el
 
 int cvo_last_pattern(cvo_handle *h, int32_t *ij, float *a, int cap, int *n) {
     if (!h || !h->aws || !n) return CVO_ERR_INVALID;
-    int nf = 0;
-    int rc = cvo_slot_size(h, CVO_SLOT_FIXED, &nf);
-    if (rc != CVO_OK) return rc;
-    return align_last_pattern(h->aws, nf, ij, a, cap, n, h->stream);
+    return align_last_pattern(h->aws, h->last_nnz, ij, a, cap, n, h->stream);
 }
 
 static int handle_query(cvo_handle *h, int slot_a, const float *Ta, int slot_b, int kind, QueryOut *res) {

@@ -98,7 +98,7 @@ int align_run(AlignWorkspace *ws, const cvo_params &prm, int n_tasks, const Alig
               cvo_align_result *results_dev, cvo_iter_record *trace_dev, int trace_cap,
               bool single_iteration, cudaStream_t stream, int64_t *launch_counter);
 // debug: in-cutoff pattern left in workgroup 0's scratch by the last run (host arrays)
-int align_last_pattern(AlignWorkspace *ws, int n_fixed, int32_t *ij, float *a, int cap, int *n,
+int align_last_pattern(AlignWorkspace *ws, int nnz, int32_t *ij, float *a, int cap, int *n,
                        cudaStream_t stream);
 // cumulative {kernel evals, iterations, sum of nnz over iterations}
 void align_ws_stats(AlignWorkspace *ws, cudaStream_t stream, int64_t out[3]);

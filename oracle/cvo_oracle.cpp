@@ -417,11 +417,16 @@ void create_pointcloud(const uint8_t *bgr, size_t bgr_stride, const uint16_t *de
 // ---------------------------------------------------------------------------------------------
 // Order-independent summation.  The reference forms each row's flow contribution as an Eigen
 // float dot product `(1/c*Ai)*cross_xy` (cvo.cpp:222-223) whose summation order is an
-// implementation detail of Eigen's vectorised redux, and adds the row results into a double
-// under a spin lock in scheduling order (cvo.cpp:226-230).  The oracle takes the canonical
-// representative of all those orders: the exact sum, rounded once.  Exact sums are kept in a
-// two-limb fixed-point accumulator (value = hi*2^-36 + lo*2^-84): adding is associative, so the
-// CUDA path can reproduce the same bits with any parallel decomposition.
+// implementation detail of Eigen's vectorised redux, and adds the row results — and the row sums
+// Bi..Ei of compute_step_size — into doubles under a spin lock in TBB scheduling order
+// (cvo.cpp:226-230, 309-314): its omega, v, B..E are only defined up to that order (~1e-7 and
+// ~1e-16 relative).  The oracle takes the canonical representative of all admissible orders:
+// the exact sum of the terms, rounded once.
+//   * flow terms are products of two floats (exact in double); they are summed exactly in a
+//     two-limb fixed-point accumulator (value = hi*2^-36 + lo*2^-84), an associative integer sum;
+//   * B..E terms are doubles; they are summed in double-double (error ~1e-32 relative), whose
+//     rounding to double is the correctly rounded exact sum for all practical purposes.
+// Being order-free, both can be reproduced bit for bit by any parallel decomposition on the GPU.
 // ---------------------------------------------------------------------------------------------
 struct ExactAcc {
     long long hi = 0, lo = 0;
@@ -433,6 +438,20 @@ struct ExactAcc {
     }
     inline void add(const ExactAcc &o) { hi += o.hi; lo += o.lo; }
     inline double value() const { return (double)hi * 0x1p-36 + (double)lo * 0x1p-84; }
+};
+
+struct DDAcc {   // double-double running sum (TwoSum + low-order accumulation)
+    double hi = 0, lo = 0;
+    inline void add(double t) {
+        double a = hi;
+        double sum = a + t;
+        double bb = sum - a;
+        double err = (a - (sum - bb)) + (t - bb);
+        hi = sum;
+        lo += err;
+    }
+    inline void add(const DDAcc &o) { add(o.hi); lo += o.lo; }
+    inline double value() const { return hi + lo; }
 };
 
 // sin/cos of a float argument, correctly rounded to float (the reference calls std::sin(float)
@@ -849,8 +868,6 @@ struct OracleCvo {
             ExactAcc lw[3], lv[3];
 #pragma omp for schedule(static) nowait
             for (int i = 0; i < fx.n; i++) {
-                if (row_ptr[i] == row_ptr[i + 1]) continue;   // an empty row contributes exact zeros
-                ExactAcc rw[3], rv[3];
                 for (int t = row_ptr[i]; t < row_ptr[i + 1]; t++) {
                     const V3 &x = fx.pos[i];
                     const V3 &y = cloud_y[trips[t].j];
@@ -859,15 +876,9 @@ struct OracleCvo {
                     float va = inv_d * trips[t].a;
                     for (int k = 0; k < 3; k++) {
                         float df = y[k] - x[k];
-                        rw[k].add((double)wa * (double)cr[k]);   // products of two floats: exact in double
-                        rv[k].add((double)va * (double)df);
+                        lw[k].add((double)wa * (double)cr[k]);   // products of two floats: exact in double
+                        lv[k].add((double)va * (double)df);
                     }
-                }
-                for (int k = 0; k < 3; k++) {
-                    float pw = (float)rw[k].value();   // the row's float dot product, .cast<double>()
-                    float pv = (float)rv[k].value();
-                    lw[k].add((double)pw);
-                    lv[k].add((double)pv);
                 }
             }
 #pragma omp critical
@@ -905,12 +916,11 @@ struct OracleCvo {
         float m2tc = (float)(-2.0 * temp_coef);
         float p2tc = (float)(2.0 * temp_coef);
         float mtc = -temp_coef;
-        // per-row sums (cvo.cpp:277-306), then rows added in ascending order: the reference adds them
-        // under a spin lock in scheduling order; a fixed order keeps the oracle machine-independent
-        std::vector<double> rB(fx.n, 0.0), rC(fx.n, 0.0), rD(fx.n, 0.0), rE(fx.n, 0.0);
+        // terms of cvo.cpp:301-305, summed in double-double (order-free, see DDAcc)
+        std::vector<DDAcc> rB(fx.n), rC(fx.n), rD(fx.n), rE(fx.n);
 #pragma omp parallel for schedule(static)
         for (int i = 0; i < fx.n; i++) {  // :275-315
-            double Bi = 0, Ci = 0, Di = 0, Ei = 0;
+            DDAcc Bi, Ci, Di, Ei;
             for (int t = row_ptr[i]; t < row_ptr[i + 1]; t++) {
                 int idx = trips[t].j;
                 const V3 &x = fx.pos[i];
@@ -924,16 +934,17 @@ struct OracleCvo {
                 float epsil_ij = mtc * (epsil_const[idx] + 2.0f * dot3(xi4z[idx], diff));
                 float A_ij = trips[t].a;
                 // the RHS below is evaluated in double where the reference's literals are double
-                Bi += double(A_ij * beta_ij);
-                Ci += double(A_ij * (gamma_ij + beta_ij * beta_ij / 2.0));
-                Di += double(A_ij * (delta_ij + beta_ij * gamma_ij + beta_ij * beta_ij * beta_ij / 6.0));
-                Ei += double(A_ij * (epsil_ij + beta_ij * delta_ij + 1 / 2.0 * beta_ij * beta_ij * gamma_ij +
-                                     1 / 2.0 * gamma_ij * gamma_ij + 1 / 24.0 * beta_ij * beta_ij * beta_ij * beta_ij));
+                Bi.add(double(A_ij * beta_ij));
+                Ci.add(double(A_ij * (gamma_ij + beta_ij * beta_ij / 2.0)));
+                Di.add(double(A_ij * (delta_ij + beta_ij * gamma_ij + beta_ij * beta_ij * beta_ij / 6.0)));
+                Ei.add(double(A_ij * (epsil_ij + beta_ij * delta_ij + 1 / 2.0 * beta_ij * beta_ij * gamma_ij +
+                                      1 / 2.0 * gamma_ij * gamma_ij + 1 / 24.0 * beta_ij * beta_ij * beta_ij * beta_ij)));
             }
             rB[i] = Bi; rC[i] = Ci; rD[i] = Di; rE[i] = Ei;
         }
-        double B = 0, C = 0, D = 0, E = 0;
-        for (int i = 0; i < fx.n; i++) { B += rB[i]; C += rC[i]; D += rD[i]; E += rE[i]; }
+        DDAcc sB, sC, sD, sE;
+        for (int i = 0; i < fx.n; i++) { sB.add(rB[i]); sC.add(rC[i]); sD.add(rD[i]); sE.add(rE[i]); }
+        double B = sB.value(), C = sC.value(), D = sD.value(), E = sE.value();
         cB = B; cC = C; cD = D; cE = E;
         // :317-333
         float p0 = 4.0 * float(E), p1 = 3.0 * float(D), p2 = 2.0 * float(C), p3 = float(B);
