@@ -432,3 +432,39 @@ def test_tracking_sequence_parity(cuda_api, oracle_api, tum_calib):
         assert c["r_odometry"]["cos_angle"] == pytest.approx(o["r_odometry"]["cos_angle"], rel=INNER_RTOL)
         Hc, Ho = c["r_odometry"]["post_hessian"], o["r_odometry"]["post_hessian"]
         assert np.allclose(Hc, Ho, rtol=0, atol=1e-4 * np.abs(Ho).max())
+
+
+def test_cpp_dropin_matches_python_path(cuda_api, tum_calib, pair_c1, tmp_path):
+    """The C++ drop-in class (include/cvo.hpp) driven like LocalTracker gives the same bits as the
+    ctypes path: same library, same kernels."""
+    import os
+    import subprocess
+    from test_host_logic import _build_dropin
+    from cvo_slam_b200 import cvo as cvo_mod
+    bgr_a, d_a, bgr_b, d_b, _ = pair_c1
+    exe = _build_dropin(tmp_path)
+    files = []
+    for name, arr in (("a_bgr", bgr_a), ("a_d", d_a), ("b_bgr", bgr_b), ("b_d", d_b)):
+        p = os.path.join(str(tmp_path), name + ".raw")
+        arr.tofile(p)
+        files.append(p)
+    calib = os.path.join(str(tmp_path), "calib.yaml")
+    with open(calib, "w") as f:
+        f.write("%YAML:1.0\nCamera.fx: 517.306408\nCamera.fy: 516.469215\nCamera.cx: 318.643040\n"
+                "Camera.cy: 255.313989\nDepthMapFactor: 5000.0\n")
+    out = subprocess.run([exe, calib] + files + ["640", "480"], capture_output=True, text=True, check=True).stdout
+    assert "cvo not initialized !" in out
+    lines = {l.split()[0]: l.split()[1:] for l in out.splitlines() if l and l.split()[0] in ("N", "T", "inn")}
+    c = cvo_mod.Cvo(tum_calib, api=cuda_api)
+    c.set_pcd(bgr_a, d_a)
+    T = c.match_odometry(bgr_b, d_b)
+    r = c.compute_innerproduct(T.astype(np.float32))
+    assert [int(lines["N"][0]), int(lines["N"][1])] == list(c.get_fixed_and_moving_number())
+    assert int(lines["N"][3]) == c.get_A_nonzero() and int(lines["N"][5]) == c.get_iteration_number()
+    Tc = np.array([float(x) for x in lines["T"]], np.float32).reshape(4, 4)
+    assert np.array_equal(Tc, c.transform)
+    inn = [float(x) for x in lines["inn"][:4]]
+    ref = [r["inn_pre"].value, r["inn_post"].value, r["inn_fixed_pcd"].value, r["inn_moving_pcd"].value]
+    assert np.allclose(inn, ref, rtol=1e-6)
+    assert "after update_fixed_pcd N %d 0" % c.get_fixed_and_moving_number()[1] in out
+    c.close()

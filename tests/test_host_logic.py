@@ -142,3 +142,28 @@ def test_track_sequence_on_oracle(oracle_api, tum_calib):
         ang, dist = pose_error(o["keyframe"], gt_kf)
         assert ang < 8e-3 and dist < 8e-3, ("keyframe", k, ang, dist)
         assert 0 < o["r_odometry"]["cos_angle"] <= 1.01
+
+
+def _build_dropin(tmp_path):
+    from cvo_slam_b200 import build, capi
+    build.build()
+    exe = os.path.join(str(tmp_path), "dropin_smoke")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "dropin_smoke.cpp"), "-o", exe, "-L", libdir, "-lcvo_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_cpp_dropin_header_compiles_and_links(tmp_path):
+    """include/cvo.hpp (the drop-in `cvo::cvo`) compiles against the C ABI and links to the library."""
+    exe = _build_dropin(tmp_path)
+    assert os.path.exists(exe)
+    src = open(os.path.join(ROOT, "include", "cvo.hpp")).read()
+    for name in ("set_pcd", "match_odometry", "match_keyframe", "align", "function_inner_product",
+                 "compute_innerproduct", "compute_innerproduct_lc", "se3_Hessian", "update_fixed_pcd",
+                 "update_previous_pcd", "reset_keyframe", "reset_transform", "reset_initial",
+                 "get_fixed_and_moving_number", "get_iteration_number", "get_A_nonzero",
+                 "get_fixed_frame_selected_points", "get_moving_frame_selected_points",
+                 "first_frame", "prev_transform", "accum_transform"):
+        assert name in src, name
