@@ -329,6 +329,12 @@ class CudaLowLevel(LowLevel):
         self._check(self.lib.cvo_set_frame_device(h, slot, bgr_ptr, depth_ptr, w, hgt),
                     "set_frame_device")
 
+    def phase_cycles(self, h):
+        s = (C.c_int64 * 6)()
+        self.lib.cvo_handle_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        self._check(self.lib.cvo_handle_phase_cycles(h, s), "handle_phase_cycles")
+        return dict(zip(("grid", "P0", "P1a", "P1b", "P2", "P3"), [int(x) for x in s]))
+
     def handle_stats(self, h):
         s = (C.c_int64 * 4)()
         self._check(self.lib.cvo_handle_stats(h, s), "handle_stats")

@@ -477,6 +477,19 @@ int cvo_handle_stats(cvo_handle *h, int64_t stats[4]) {
     return CVO_OK;
 }
 
+int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[6]) {
+    if (!h || !cycles) return CVO_ERR_INVALID;
+    for (int i = 0; i < 6; i++) cycles[i] = 0;
+    if (h->aws) align_ws_phase_cycles(h->aws, h->stream, cycles);
+    return CVO_OK;
+}
+
+int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[6]) {
+    if (!b || !cycles) return CVO_ERR_INVALID;
+    align_ws_phase_cycles(b->aws, b->stream, cycles);
+    return CVO_OK;
+}
+
 // ---- batches -----------------------------------------------------------------------------------
 
 int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int device, int max_frames, int max_pairs,

@@ -181,6 +181,10 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
  * align iterations, stored non-zeros summed over iterations} */
 int cvo_batch_stats(cvo_batch *b, int64_t stats[4]);
 int cvo_handle_stats(cvo_handle *h, int64_t stats[4]);
+/* cumulative SM cycles (thread 0 of every CTA) per phase of the align kernel:
+ * {grid build, P0 transform, P1a neighbour search, P1b kernel values + flow, P2 step coefficients, P3 scalar update} */
+int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[6]);
+int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[6]);
 /* device-time of the last cvo_batch_align's kernel in ms (CUDA events on its stream) */
 int cvo_batch_last_align_ms(cvo_batch *b, float *ms);
 /* CUDA events on the batch's own stream (the stream every kernel of the batch is launched on):
