@@ -124,9 +124,25 @@ static int handle_ensure_arena(cvo_handle *h, int need_cap) {
     return CVO_OK;
 }
 
+// The align scratch is sized by the largest cloud it has to hold.  For ordinary clouds that is the
+// arena capacity (no synchronisation); for large arenas (dense selection) the actual point
+// counts are read back so that the scratch follows the data, not the worst case.
 static int handle_ensure_aws(cvo_handle *h) {
-    if (h->aws) return CVO_OK;
-    return align_ws_create(&h->aws, h->arena.cap, h->device);
+    int need = h->arena.cap;
+    if (h->arena.cap > 8192) {
+        int n[3] = {0, 0, 0};
+        CVO_CUDA_TRY(cudaMemcpyAsync(n, h->arena.n, sizeof(n), cudaMemcpyDeviceToHost, h->stream));
+        CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        int m = 0;
+        for (int s = 0; s < 3; s++)
+            if (h->slot_idx[s] >= 0 && n[h->slot_idx[s]] > m) m = n[h->slot_idx[s]];
+        need = m + m / 4 + 256;
+        if (need > h->arena.cap) need = h->arena.cap;
+        if (need < 4096) need = 4096;
+    }
+    if (h->aws && align_ws_max_points(h->aws) >= need) return CVO_OK;
+    if (h->aws) { CVO_CUDA_TRY(cudaStreamSynchronize(h->stream)); align_ws_destroy(h->aws); h->aws = nullptr; }
+    return align_ws_create(&h->aws, need, h->device);
 }
 
 static int handle_slot_arena_index(cvo_handle *h, int slot) {

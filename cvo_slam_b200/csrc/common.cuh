@@ -92,6 +92,7 @@ struct AlignTask {          // one frame pair
 struct AlignWorkspace;      // opaque scratch for `n_workgroups` concurrent pairs
 int align_ws_create(AlignWorkspace **ws, int max_points, int device);
 void align_ws_destroy(AlignWorkspace *ws);
+int align_ws_max_points(const AlignWorkspace *ws);
 // Runs tasks[0..n) (device array) -> results[0..n) (device array).  trace may be null.
 // single_iteration: evaluate exactly one compute_flow + compute_step_size, do not update.
 int align_run(AlignWorkspace *ws, const cvo_params &prm, int n_tasks, const AlignTask *tasks_dev,

@@ -468,3 +468,33 @@ def test_cpp_dropin_matches_python_path(cuda_api, tum_calib, pair_c1, tmp_path):
     assert np.allclose(inn, ref, rtol=1e-6)
     assert "after update_fixed_pcd N %d 0" % c.get_fixed_and_moving_number()[1] in out
     c.close()
+
+
+def test_dense_c3_parity(cuda_api, oracle_plain, tum_calib):
+    """C3: dense selection (num_want = 60000 -> pot 1, ~18 k points per frame, ~1.4 M non-zeros at
+    ell = 0.15).  Exercises the large-cloud scratch sizing and the cluster path."""
+    from cvo_slam_b200 import synth
+    a, da, b, db, T_gt = synth.make_pair(3, tum_calib, high_gradient=True, rot_deg=0.8, trans=(0.015, -0.01, 0.012))
+    p = cuda_api.default_params()
+    p.num_want = 60000
+    hc, ho = cuda_api.create(tum_calib, p), oracle_plain.create(tum_calib, p, search=0)
+    for api, h in ((cuda_api, hc), (oracle_plain, ho)):
+        api.set_frame(h, 0, a, da)
+        api.set_frame(h, 1, b, db)
+    n = cuda_api.slot_size(hc, 0)
+    assert n == oracle_plain.slot_size(ho, 0) and n > 15000
+    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    rc = cuda_api.iteration_at(hc, I, z, 0.15)
+    ro = oracle_plain.iteration_at(ho, I, z, 0.15)
+    assert rc["nnz"] == ro["nnz"] > 1000000
+    assert np.array_equal(rc["omega"], ro["omega"]) and np.array_equal(rc["v"], ro["v"])
+    assert rc["step"] == pytest.approx(ro["step"], rel=1e-6)
+    res_c, _ = cuda_api.align(hc)
+    res_o, _ = oracle_plain.align(ho)
+    assert res_c.status == 0
+    ang, dist = pose_error(res_c.transform_np(), res_o.transform_np())
+    print("C3 dense: N", n, "iterations", res_c.iterations, res_o.iterations, "pose diff", ang, dist)
+    assert res_c.iterations == res_o.iterations
+    assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
+    cuda_api.destroy(hc)
+    oracle_plain.destroy(ho)
