@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded CPU sample")
     ap.add_argument("--exp-mode", type=int, default=0, help="0 exact (bit-faithful), 1 MUFU fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sequence-frames", type=int, default=300,
+                    help="C2: frames of the sequential-tracking side measurement (N=1 only; 0 = skip)")
     return ap.parse_args()
 
 
@@ -184,6 +186,40 @@ def cpu_leg(pairs, poses, R0, T0, seed, n_pairs, steps, warmup, device):
                 sample=f"{len(sample)} pairs over {len(frame_ids)} keyframes of the same workload, "
                        f"{steps} timed repetitions; oracle/{'_ref nanoflann KD-tree' if orc.has_nanoflann else 'cell-list'} "
                        f"radius search, OpenMP over points"), per_step * 1e3
+
+
+def sequence_leg(n_frames, api, device, cpu_frames=6):
+    """BASELINE configs[1]: a TUM-shaped sequence tracked frame by frame with the LocalTracker call
+    pattern (two cvo objects, persistent R/T/ell; 2 set_pcd + 2 align + 2 compute_innerproduct per
+    frame).  A dependency chain: one GPU, latency-bound.  Returns frames/s and alignments/s from host
+    images (H2D inside), beside the CPU oracle on the first few frames."""
+    from cvo_slam_b200 import capi, cvo as cvo_mod, synth
+    from conftest_free import pose_err
+    cal = capi.TUM1_CALIB()
+    scene = synth.make_scene(2)
+    poses = synth.trajectory(n_frames, 2)
+    frames = []
+    for k, P in enumerate(poses):
+        b, d = synth.render(scene, P, cal, W, H, noise_seed=20 + k, device=device)
+        frames.append(synth.to_numpy(b, d))
+    cvo_mod.track_sequence(frames[:4], cal, api=api)            # warm-up (allocations, attributes)
+    t0 = time.perf_counter()
+    out = cvo_mod.track_sequence(frames, cal, api=api)
+    dt = time.perf_counter() - t0
+    err = [pose_err(o["keyframe"], synth.relative_transform(poses[0], poses[k + 1])) for k, o in enumerate(out)]
+    res = dict(workload=f"C2: {n_frames}-frame synthetic TUM-shaped sequence, LocalTracker call pattern, 1 GPU",
+               frames_per_s=(n_frames - 1) / dt, alignments_per_s=(2 * (n_frames - 1) - 1) / dt,
+               ms_per_frame=dt / (n_frames - 1) * 1e3,
+               max_keyframe_pose_error=dict(rad=float(max(e[0] for e in err)), m=float(max(e[1] for e in err))))
+    if cpu_frames:
+        from oracle import oracle
+        orc = oracle.load()
+        t0 = time.perf_counter()
+        cvo_mod.track_sequence(frames[:cpu_frames], cal, api=orc)
+        dtc = time.perf_counter() - t0
+        res["cpu_port_frames_per_s"] = (cpu_frames - 1) / dtc
+        res["cpu_cores"] = orc.num_threads()
+    return res
 
 
 def main():
@@ -335,6 +371,9 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, 1, 0, dev)
         line["cpu_baseline"] = cb
+    if world == 1 and a.sequence_frames >= 8:
+        bt.close()
+        line["sequence_c2"] = sequence_leg(a.sequence_frames, api, dev, 0 if a.no_cpu_baseline else 6)
     print(json.dumps(line))
     bt.close()
     if world > 1:

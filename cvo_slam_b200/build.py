@@ -36,7 +36,8 @@ def build(force=False, verbose=False, extra=()):
     objs, procs = [], []
     for src, flags in SOURCES.items():
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + flags + list(extra) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + flags + list(extra) + os.environ.get("CVO_NVCC_EXTRA", "").split() + \
+            ["-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             print(" ".join(cmd))
         procs.append((cmd, subprocess.Popen(cmd, env=env)))

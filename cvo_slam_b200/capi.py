@@ -330,10 +330,24 @@ class CudaLowLevel(LowLevel):
                     "set_frame_device")
 
     def phase_cycles(self, h):
-        s = (C.c_int64 * 6)()
+        s = (C.c_int64 * 8)()
         self.lib.cvo_handle_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         self._check(self.lib.cvo_handle_phase_cycles(h, s), "handle_phase_cycles")
-        return dict(zip(("grid", "P0", "P1a", "P1b", "P2", "P3"), [int(x) for x in s]))
+        return dict(zip(("grid", "P0", "P1a", "P1b", "P2", "P3", "retest", "rebuilds"), [int(x) for x in s]))
+
+    def compute_innerproduct(self, h, tran):
+        """cvo_compute_innerproduct: ((value, num) x 4, H, inliers) in one launch"""
+        self.lib.cvo_compute_innerproduct.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                      C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        T = _f32(tran, (16,))
+        v = np.zeros(4, np.float32)
+        n = np.zeros(4, np.int32)
+        H = np.zeros(36, np.float64)
+        inl = C.c_int(0)
+        self._check(self.lib.cvo_compute_innerproduct(h, _fp(T), _fp(v), n.ctypes.data_as(C.POINTER(C.c_int)),
+                                                      H.ctypes.data_as(C.POINTER(C.c_double)), C.byref(inl)),
+                    "compute_innerproduct")
+        return [(float(v[k]), int(n[k])) for k in range(4)], H.reshape(6, 6), inl.value
 
     def handle_stats(self, h):
         s = (C.c_int64 * 4)()

@@ -439,6 +439,43 @@ int cvo_hessian(cvo_handle *h, int slot_a, const float *Ta, int slot_b, double H
     return CVO_OK;
 }
 
+// cvo::compute_innerproduct (cvo.cpp:475-503) in one launch: the four inner products and the
+// Hessian are five independent queries, one CTA each.
+int cvo_compute_innerproduct(cvo_handle *h, const float tran[16], float values[4], int nums[4], double H[36],
+                             int *inliers) {
+    if (!h || !tran || !values || !nums || !H || !inliers) return CVO_ERR_INVALID;
+    if (h->slot_idx[CVO_SLOT_FIXED] < 0 || h->slot_idx[CVO_SLOT_MOVING] < 0) return CVO_ERR_NOT_INIT;
+    CVO_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = handle_ensure_aws(h);
+    if (rc != CVO_OK) return rc;
+    QueryTask *hq = reinterpret_cast<QueryTask *>(h->pinned + 8192);
+    QueryOut *ho = reinterpret_cast<QueryOut *>(h->pinned + 16384);
+    static const float I34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const CloudView fx = h->arena.view(h->slot_idx[CVO_SLOT_FIXED]), mv = h->arena.view(h->slot_idx[CVO_SLOT_MOVING]);
+    // {inn_pre, inn_post, inn_fixed_pcd, inn_moving_pcd, post_hessian}
+    const CloudView qa[5] = {mv, mv, fx, mv, mv}, qb[5] = {fx, fx, fx, mv, fx};
+    const float *qt[5] = {I34, tran, I34, I34, tran};
+    for (int k = 0; k < 5; k++) {
+        hq[k].a = qa[k];
+        hq[k].b = qb[k];
+        memcpy(hq[k].Ta, qt[k], sizeof(hq[k].Ta));
+        hq[k].ell = h->ell;
+        hq[k].kind = k == 4 ? 1 : 0;
+    }
+    CVO_CUDA_TRY(cudaMemcpyAsync(h->d_q, hq, sizeof(QueryTask) * 5, cudaMemcpyHostToDevice, h->stream));
+    rc = query_run(h->aws, h->prm, 5, h->d_q, h->d_qo, h->stream, &h->launches);
+    if (rc != CVO_OK) return rc;
+    CVO_CUDA_TRY(cudaMemcpyAsync(ho, h->d_qo, sizeof(QueryOut) * 5, cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; k++) {
+        values[k] = (float)ho[k].sum;
+        nums[k] = ho[k].count == 0 ? 1 : ho[k].count;
+    }
+    *inliers = ho[4].count;
+    finish_hessian_host(ho[4], H);
+    return CVO_OK;
+}
+
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n) {
     if (!h || !slot_ok(slot) || !n) return CVO_ERR_INVALID;
     int m = 0;
@@ -493,14 +530,14 @@ int cvo_handle_stats(cvo_handle *h, int64_t stats[4]) {
     return CVO_OK;
 }
 
-int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[6]) {
+int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[8]) {
     if (!h || !cycles) return CVO_ERR_INVALID;
-    for (int i = 0; i < 6; i++) cycles[i] = 0;
+    for (int i = 0; i < 8; i++) cycles[i] = 0;
     if (h->aws) align_ws_phase_cycles(h->aws, h->stream, cycles);
     return CVO_OK;
 }
 
-int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[6]) {
+int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[8]) {
     if (!b || !cycles) return CVO_ERR_INVALID;
     align_ws_phase_cycles(b->aws, b->stream, cycles);
     return CVO_OK;

@@ -103,7 +103,7 @@ int align_last_pattern(AlignWorkspace *ws, int nnz, int32_t *ij, float *a, int c
                        cudaStream_t stream);
 // cumulative {kernel evals, iterations, sum of nnz over iterations}
 void align_ws_stats(AlignWorkspace *ws, cudaStream_t stream, int64_t out[3]);
-void align_ws_phase_cycles(AlignWorkspace *ws, cudaStream_t stream, int64_t out[6]);
+void align_ws_phase_cycles(AlignWorkspace *ws, cudaStream_t stream, int64_t out[8]);
 
 struct QueryTask {          // <Ta * a, b> at `ell`
     CloudView a, b;

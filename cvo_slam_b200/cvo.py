@@ -101,6 +101,13 @@ class Cvo:
         """-> dict(inn_pre, inn_post, post_hessian, inliers, inn_fixed_pcd, inn_moving_pcd, cos_angle)"""
         a = self.api
         tran = np.asarray(tran, dtype=np.float32)
+        if hasattr(a, "compute_innerproduct"):   # one launch for the five queries (CUDA library)
+            vals, H, inliers = a.compute_innerproduct(self.h, tran)
+            inn_pre, inn_post, inn_fixed, inn_moving = (InnP(*v) for v in vals)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cos_angle = np.float32(inn_post.value / (np.sqrt(inn_fixed.value) * np.sqrt(inn_moving.value)))
+            return dict(inn_pre=inn_pre, inn_post=inn_post, post_hessian=H, inliers=inliers,
+                        inn_fixed_pcd=inn_fixed, inn_moving_pcd=inn_moving, cos_angle=cos_angle)
         inn_pre = InnP(*a.inner_product(self.h, SLOT_MOVING, None, SLOT_FIXED))
         inn_post = InnP(*a.inner_product(self.h, SLOT_MOVING, tran, SLOT_FIXED))
         inn_fixed = InnP(*a.inner_product(self.h, SLOT_FIXED, None, SLOT_FIXED))

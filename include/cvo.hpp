@@ -307,14 +307,17 @@ public:
     /* cvo.cpp:475-503 */
     void compute_innerproduct(inn_p &inn_pre, inn_p &inn_post, matrix66d_t &post_hessian, affine3f_t &tran,
                               int &inliers, inn_p &inn_fixed_pcd, inn_p &inn_moving_pcd, float &cos_angle) {
-        float T[16];
+        float T[16], v[4];
+        int n[4];
+        double H[36];
         detail::to_rows(tran, T);
-        inn_pre.copy(inner(CVO_SLOT_MOVING, nullptr, CVO_SLOT_FIXED));
-        inn_post.copy(inner(CVO_SLOT_MOVING, T, CVO_SLOT_FIXED));
-        inn_fixed_pcd.copy(inner(CVO_SLOT_FIXED, nullptr, CVO_SLOT_FIXED));
-        inn_moving_pcd.copy(inner(CVO_SLOT_MOVING, nullptr, CVO_SLOT_MOVING));
+        check(cvo_compute_innerproduct(h_, T, v, n, H, &inliers), "cvo_compute_innerproduct");
+        inn_pre.copy(inn_p(v[0], n[0], 0));
+        inn_post.copy(inn_p(v[1], n[1], 0));
+        inn_fixed_pcd.copy(inn_p(v[2], n[2], 0));
+        inn_moving_pcd.copy(inn_p(v[3], n[3], 0));
         cos_angle = inn_post.value / (std::sqrt(inn_fixed_pcd.value) * std::sqrt(inn_moving_pcd.value));
-        post_hessian = hess(CVO_SLOT_MOVING, T, CVO_SLOT_FIXED, inliers);
+        for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) post_hessian(r, c) = H[r * 6 + c];
     }
 
     /* cvo.cpp:505-561 */

@@ -143,6 +143,12 @@ int cvo_inner_product(cvo_handle *h, int slot_a, const float *Ta, int slot_b, fl
 int cvo_hessian(cvo_handle *h, int slot_a, const float *Ta, int slot_b, double H[36],
                 int *inliers);
 
+/* replaces the body of cvo::compute_innerproduct (cvo.cpp:475-503) in one launch:
+ * values/nums = {inn_pre, inn_post, inn_fixed_pcd, inn_moving_pcd}, H = post_hessian; tran is the
+ * 4x4 row-major transform applied to the moving cloud for inn_post and the Hessian. */
+int cvo_compute_innerproduct(cvo_handle *h, const float tran[16], float values[4], int nums[4],
+                             double H[36], int *inliers);
+
 /* replaces get_{fixed,moving}_frame_selected_points (cvo.hpp:275-276): xy pairs */
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n);
 /* positions n x 3, features n x 5 row-major (tests, and host point_cloud mirrors) */
@@ -182,9 +188,10 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
 int cvo_batch_stats(cvo_batch *b, int64_t stats[4]);
 int cvo_handle_stats(cvo_handle *h, int64_t stats[4]);
 /* cumulative SM cycles (thread 0 of every CTA) per phase of the align kernel:
- * {grid build, P0 transform, P1a neighbour search, P1b kernel values + flow, P2 step coefficients, P3 scalar update} */
-int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[6]);
-int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[6]);
+ * {grid build, P0 transform, P1a neighbour search, P1b kernel values + flow, P2 step coefficients,
+ * P3 scalar update, P1a list re-test}, then the number of neighbour-list rebuilds */
+int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[8]);
+int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[8]);
 /* device-time of the last cvo_batch_align's kernel in ms (CUDA events on its stream) */
 int cvo_batch_last_align_ms(cvo_batch *b, float *ms);
 /* CUDA events on the batch's own stream (the stream every kernel of the batch is launched on):
