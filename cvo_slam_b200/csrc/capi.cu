@@ -560,7 +560,7 @@ int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int devic
     cudaError_t e = cudaSuccess;
     if (rc == CVO_OK) rc = sel_create(&b->sel[0], width, height, b->chunk);
     if (rc == CVO_OK) rc = sel_create(&b->sel[1], width, height, b->chunk);
-    if (rc == CVO_OK) rc = align_ws_create(&b->aws, b->arena.cap, device);
+    if (rc == CVO_OK) rc = align_ws_create(&b->aws, b->arena.cap < 65536 ? b->arena.cap : 65536, device);
     if (rc == CVO_OK) {
         e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
