@@ -87,7 +87,7 @@ def pair_priors(pairs, poses, seed):
     return R, T, gts
 
 
-def render_frames(frame_ids, poses, seed, device):
+def render_frames(frame_ids, poses, seed, device, noise_salt=0):
     """-> (bgr uint8 [n,H,W,3], depth uint16 [n,H,W]) torch tensors on `device`."""
     import torch
     from cvo_slam_b200 import capi, synth
@@ -96,7 +96,7 @@ def render_frames(frame_ids, poses, seed, device):
     bgr = torch.empty((len(frame_ids), H, W, 3), dtype=torch.uint8, device=device)
     dep = torch.empty((len(frame_ids), H, W), dtype=torch.int16, device=device)   # uint16 bit pattern
     for k, f in enumerate(frame_ids):
-        b, d = synth.render(scene, poses[f], cal, W, H, noise_seed=seed * 100003 + f, device=device)
+        b, d = synth.render(scene, poses[f], cal, W, H, noise_seed=seed * 100003 + f + 7919 * noise_salt, device=device)
         bgr[k] = b
         dep[k] = d.view(torch.int16)
     return bgr, dep
@@ -228,7 +228,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_frames, n_pairs = a.frames, a.frames * a.partners
-    seed = 1000 + rank
+    # weak scaling: every rank gets the same scene, keyframe poses and priors (statistically
+    # identical work per GPU); only the sensor noise of the rendered frames differs per rank
+    seed = 1000
     poses = keyframe_poses(n_frames, seed)
     pairs = pair_list(n_frames, a.partners)
     R0, T0, gts = pair_priors(pairs, poses, seed)
@@ -265,7 +267,7 @@ def main():
     prm = api.default_params()
     prm.exp_mode = a.exp_mode
 
-    bgr_d, dep_d = render_frames(list(range(n_frames)), poses, seed, dev)
+    bgr_d, dep_d = render_frames(list(range(n_frames)), poses, seed, dev, noise_salt=rank)
     torch.cuda.synchronize()
     bt = B.Batch(cal, prm, max_frames=n_frames, max_pairs=n_pairs, width=W, height=H, device=local_rank, api=api)
     desc = bt.make_pairs(pairs, R0.reshape(-1, 3, 3), T0, prm.ell_init)
@@ -328,7 +330,12 @@ def main():
     status_bad = int((res["status"] != 0).sum())
 
     ms_step = t_dev / a.steps
+    rank_ms = [ms_step]
     if world > 1:
+        mine = torch.tensor([ms_step, t_align / a.steps], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [[round(float(x[0]), 2), round(float(x[1]), 2)] for x in allr]
         t = torch.tensor([ms_step, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_s = float(t[0]), float(t[1])
@@ -366,7 +373,7 @@ def main():
                          h2d_bytes_per_step=int(n_frames * W * H * 5 + desc.nbytes * 2),
                          d2h_bytes_per_step=int(res.nbytes + n_pairs * 192)),
                 gpu_launches=int(launches * a.steps), roofline=roofline,
-                wall_ms_per_step=wall / a.steps * 1e3,
+                wall_ms_per_step=wall / a.steps * 1e3, per_rank_ms_step_and_align=rank_ms,
                 check=dict(median_translation_error_m=float(np.median(err)), pairs_with_error_status=status_bad))
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, 1, 0, dev)
