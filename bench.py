@@ -194,7 +194,6 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
     frame).  A dependency chain: one GPU, latency-bound.  Returns frames/s and alignments/s from host
     images (H2D inside), beside the CPU oracle on the first few frames."""
     from cvo_slam_b200 import capi, cvo as cvo_mod, synth
-    from conftest_free import pose_err
     cal = capi.TUM1_CALIB()
     scene = synth.make_scene(2)
     poses = synth.trajectory(n_frames, 2)
@@ -206,7 +205,7 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
     t0 = time.perf_counter()
     out = cvo_mod.track_sequence(frames, cal, api=api)
     dt = time.perf_counter() - t0
-    err = [pose_err(o["keyframe"], synth.relative_transform(poses[0], poses[k + 1])) for k, o in enumerate(out)]
+    err = [synth.pose_error(o["keyframe"], synth.relative_transform(poses[0], poses[k + 1])) for k, o in enumerate(out)]
     res = dict(workload=f"C2: {n_frames}-frame synthetic TUM-shaped sequence, LocalTracker call pattern, 1 GPU",
                frames_per_s=(n_frames - 1) / dt, alignments_per_s=(2 * (n_frames - 1) - 1) / dt,
                ms_per_frame=dt / (n_frames - 1) * 1e3,

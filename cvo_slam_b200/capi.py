@@ -320,6 +320,10 @@ class CudaLowLevel(LowLevel):
                     "create")
         return h
 
+    def copy_cloud(self, dst, dst_slot, src, src_slot):
+        self.lib.cvo_copy_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self._check(self.lib.cvo_copy_cloud(dst, dst_slot, src, src_slot), "copy_cloud")
+
     def random_pattern(self, n):
         out = np.zeros(n, np.uint8)
         self._check(self.lib.cvo_random_pattern(out.ctypes.data, n), "random_pattern")

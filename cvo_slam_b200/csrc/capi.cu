@@ -142,7 +142,7 @@ static int handle_ensure_aws(cvo_handle *h) {
     }
     if (h->aws && align_ws_max_points(h->aws) >= need) return CVO_OK;
     if (h->aws) { CVO_CUDA_TRY(cudaStreamSynchronize(h->stream)); align_ws_destroy(h->aws); h->aws = nullptr; }
-    return align_ws_create(&h->aws, need, h->device);
+    return align_ws_create(&h->aws, need, h->device, 8);
 }
 
 static int handle_slot_arena_index(cvo_handle *h, int slot) {
@@ -303,6 +303,30 @@ int cvo_set_cloud(cvo_handle *h, int slot, int n, const float *positions, const 
         CVO_CUDA_TRY(cudaMemcpy(h->arena.pix + o, pix.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
     }
     CVO_CUDA_TRY(cudaMemcpy(h->arena.n + k, &n, sizeof(int), cudaMemcpyHostToDevice));
+    return CVO_OK;
+}
+
+// LocalTracker feeds the same image to two cvo objects (local_tracker.cpp:356,415),
+// so the reference selects its points twice.  A caller that knows this can select once and copy the
+// device cloud (140 KB) into the other handle.
+int cvo_copy_cloud(cvo_handle *dst, int dst_slot, cvo_handle *src, int src_slot) {
+    if (!dst || !src || !slot_ok(dst_slot) || !slot_ok(src_slot)) return CVO_ERR_INVALID;
+    if (src->slot_idx[src_slot] < 0) return CVO_ERR_NOT_INIT;
+    if (dst->device != src->device) return CVO_ERR_INVALID;
+    CVO_CUDA_TRY(cudaSetDevice(src->device));
+    int rc = handle_ensure_arena(dst, src->arena.cap);
+    if (rc != CVO_OK) return rc;
+    const int kd = handle_slot_arena_index(dst, dst_slot);
+    if (kd < 0) return CVO_ERR_INVALID;
+    const int ks = src->slot_idx[src_slot];
+    CVO_CUDA_TRY(cudaStreamSynchronize(src->stream));   // the cloud may still be in flight on the source stream
+    const size_t so = (size_t)ks * src->arena.cap, d_o = (size_t)kd * dst->arena.cap, n = src->arena.cap;
+    cudaStream_t st = dst->stream;
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.pos + d_o, src->arena.pos + so, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.f03 + d_o, src->arena.f03 + so, n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.f4 + d_o, src->arena.f4 + so, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.pix + d_o, src->arena.pix + so, n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.n + kd, src->arena.n + ks, sizeof(int), cudaMemcpyDeviceToDevice, st));
     return CVO_OK;
 }
 
@@ -555,12 +579,12 @@ int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int devic
     if (params) b->prm = *params;
     else cvo_default_params(&b->prm);
     b->w = width; b->h = height; b->max_frames = max_frames; b->max_pairs = max_pairs;
-    b->chunk = max_frames < 32 ? max_frames : 32;
+    b->chunk = max_frames < 148 ? max_frames : 148;   // one k_compact CTA per frame: a chunk fills the SMs
     int rc = arena_alloc(b->arena, max_frames, cloud_capacity_for(b->prm, width, height));
     cudaError_t e = cudaSuccess;
     if (rc == CVO_OK) rc = sel_create(&b->sel[0], width, height, b->chunk);
     if (rc == CVO_OK) rc = sel_create(&b->sel[1], width, height, b->chunk);
-    if (rc == CVO_OK) rc = align_ws_create(&b->aws, b->arena.cap < 65536 ? b->arena.cap : 65536, device);
+    if (rc == CVO_OK) rc = align_ws_create(&b->aws, b->arena.cap < 65536 ? b->arena.cap : 65536, device, 0);
     if (rc == CVO_OK) {
         e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);

@@ -129,6 +129,13 @@ def relative_transform(T_wa, T_wb):
     return np.linalg.inv(np.asarray(T_wa)) @ np.asarray(T_wb)
 
 
+def pose_error(T_est, T_ref):
+    """(rotation angle in rad, translation distance in m) between two 4x4 transforms."""
+    E = np.linalg.inv(np.asarray(T_ref, np.float64)) @ np.asarray(T_est, np.float64)
+    ang = float(np.arccos(np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)))
+    return ang, float(np.linalg.norm(E[:3, 3]))
+
+
 def make_pair(seed, calib, w=640, h=480, rot_deg=1.0, axis=(0.3, 1.0, 0.2), trans=(0.02, -0.01, 0.015),
               high_gradient=False, device="cpu", noise_sigma=2.0):
     """C1-style pair: frame a at the origin pose, frame b offset by a known SE(3).

@@ -116,6 +116,9 @@ int cvo_set_cloud(cvo_handle *h, int slot, int n, const float *positions, const 
  * reset_keyframe (cvo.cpp:578-604): dst <- src, src becomes empty. */
 int cvo_slot_move(cvo_handle *h, int dst, int src);
 int cvo_slot_size(cvo_handle *h, int slot, int *n);
+/* copies the device cloud of (src, src_slot) into (dst, dst_slot): lets a caller that feeds one image to
+ * two cvo objects (src/local_tracker.cpp:356,415) run the point selection once */
+int cvo_copy_cloud(cvo_handle *dst, int dst_slot, cvo_handle *src, int src_slot);
 
 /* state that persists between align() calls (cvo.hpp:103,122-123) */
 int cvo_set_RT(cvo_handle *h, const float R[9], const float T[3]);

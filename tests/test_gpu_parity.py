@@ -498,3 +498,23 @@ def test_dense_c3_parity(cuda_api, oracle_plain, tum_calib):
     assert ang < POSE_TOL_RAD and dist < POSE_TOL_M
     cuda_api.destroy(hc)
     oracle_plain.destroy(ho)
+
+
+def test_copy_cloud_between_handles(cuda_api, tum_calib, pair_c1):
+    """cvo_copy_cloud: select once, share the device cloud with a second object."""
+    bgr_a, d_a, bgr_b, d_b, _ = pair_c1
+    h1, h2 = cuda_api.create(tum_calib), cuda_api.create(tum_calib)
+    cuda_api.set_frame(h1, 0, bgr_a, d_a)
+    cuda_api.set_frame(h1, 1, bgr_b, d_b)
+    cuda_api.copy_cloud(h2, 0, h1, 0)
+    cuda_api.copy_cloud(h2, 1, h1, 1)
+    for slot in (0, 1):
+        p1, f1 = cuda_api.get_cloud(h1, slot)
+        p2, f2 = cuda_api.get_cloud(h2, slot)
+        assert np.array_equal(p1, p2) and np.array_equal(f1, f2)
+        assert np.array_equal(cuda_api.get_selected_points(h1, slot), cuda_api.get_selected_points(h2, slot))
+    r1, _ = cuda_api.align(h1)
+    r2, _ = cuda_api.align(h2)
+    assert np.array_equal(r1.transform_np(), r2.transform_np()) and r1.iterations == r2.iterations
+    cuda_api.destroy(h1)
+    cuda_api.destroy(h2)
