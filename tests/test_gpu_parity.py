@@ -518,3 +518,74 @@ def test_copy_cloud_between_handles(cuda_api, tum_calib, pair_c1):
     assert np.array_equal(r1.transform_np(), r2.transform_np()) and r1.iterations == r2.iterations
     cuda_api.destroy(h1)
     cuda_api.destroy(h2)
+
+
+def test_two_handles_from_two_threads(cuda_api, tum_calib, pair_c1):
+    """Distinct handles are independent (one stream each) and may be driven concurrently, like the
+    loop-closure object on the optimisation thread (keyframe_graph.cpp:151-154)."""
+    import threading
+    bgr_a, d_a, bgr_b, d_b, _ = pair_c1
+    out = {}
+
+    def work(name):
+        h = cuda_api.create(tum_calib)
+        cuda_api.set_frame(h, 0, bgr_a, d_a)
+        cuda_api.set_frame(h, 1, bgr_b, d_b)
+        for _ in range(3):
+            cuda_api.set_RT(h, np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+            cuda_api.set_ell(h, 0.15)
+            r, _ = cuda_api.align(h)
+        out[name] = (r.transform_np(), r.iterations, cuda_api.inner_product(h, 1, r.transform_np(), 0))
+        cuda_api.destroy(h)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert len(out) == 3
+    for k in (1, 2):
+        assert np.array_equal(out[k][0], out[0][0]) and out[k][1] == out[0][1]
+        assert out[k][2][1] == out[0][2][1]
+
+
+def test_tiny_and_degenerate_clouds(cuda_api, oracle_plain, tum_calib):
+    """one-point clouds, coincident points, identical clouds: same results as the oracle."""
+    rng = np.random.default_rng(9)
+    f = rng.integers(0, 256, (64, 5)).astype(np.float32)
+    base = rng.uniform(-0.3, 0.3, (64, 3)).astype(np.float32)
+    base[:, 2] += 1.5
+    cases = [(base[:1], f[:1], base[:1] + 0.01, f[:1]),                 # single points
+             (base, f, base.copy(), f),                                  # identical clouds
+             (np.repeat(base[:4], 16, 0), f, base + 0.005, f),           # coincident fixed points
+             (base[:33], f[:33], base[:7] + 0.004, f[:7])]               # ragged sizes
+    for pa, fa_, pb, fb in cases:
+        hc, ho = cuda_api.create(tum_calib), oracle_plain.create(tum_calib, search=1)
+        for api, h in ((cuda_api, hc), (oracle_plain, ho)):
+            api.set_cloud(h, 0, pa, fa_)
+            api.set_cloud(h, 1, pb, fb)
+        rc, _ = cuda_api.align(hc)
+        ro, _ = oracle_plain.align(ho)
+        assert rc.status == 0
+        assert rc.iterations == ro.iterations and rc.A_nonzero == ro.A_nonzero
+        assert np.allclose(rc.transform_np(), ro.transform_np(), atol=1e-6)
+        vc, nc = cuda_api.inner_product(hc, 1, None, 0)
+        vo, no = oracle_plain.inner_product(ho, 1, None, 0)
+        assert nc == no and vc == pytest.approx(vo, rel=1e-4, abs=1e-12)
+        cuda_api.destroy(hc)
+        oracle_plain.destroy(ho)
+
+
+def test_invalid_arguments_return_codes(cuda_api, tum_calib):
+    import ctypes as C
+    from cvo_slam_b200.capi import CvoError
+    lib = cuda_api.lib
+    h = cuda_api.create(tum_calib)
+    assert lib.cvo_slot_move(h, 0, 7) == -1
+    assert lib.cvo_set_frame(h, 0, None, 0, None, 0, 640, 480) == -1
+    n = C.c_int(0)
+    assert lib.cvo_slot_size(h, 1, C.byref(n)) == -3          # empty slot
+    with pytest.raises(CvoError):
+        cuda_api.inner_product(h, 1, None, 0)
+    too_small = np.zeros((32, 32, 3), np.uint8)
+    with pytest.raises(CvoError):
+        cuda_api.set_frame(h, 0, too_small, np.zeros((32, 32), np.uint16))
+    cuda_api.destroy(h)
