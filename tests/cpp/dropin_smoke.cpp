@@ -52,6 +52,29 @@ int main(int argc, char **argv) {
     printf("T");
     for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) printf(" %.9g", odo.transform.matrix()(r, c));
     printf("\ninn %.9g %.9g %.9g %.9g cos %.9g H00 %.9g\n", pre.value, post.value, fx.value, mv.value, cosang, Hm(0, 0));
+    // the public upload-path wrappers (cvo.cpp:388-459, 620-759) on host clouds: same numbers as the
+    // slot-based calls made by compute_innerproduct
+    {
+        int n = 0;
+        cvo::point_cloud_t pcf, pcm;
+        for (int slot = 0; slot < 2; slot++) {
+            cvo_slot_size(odo.native_handle(), slot, &n);
+            std::vector<float> pos(3 * n), feat(5 * n);
+            cvo_get_cloud(odo.native_handle(), slot, pos.data(), feat.data(), n, &n);
+            cvo::point_cloud_t &pc = slot == 0 ? pcf : pcm;
+            pc.num_points = n;
+            pc.positions.resize(n);
+            pc.features.resize(n);
+            for (int i = 0; i < n; i++) {
+                for (int k = 0; k < 3; k++) pc.positions[i][k] = pos[3 * i + k];
+                for (int k = 0; k < 5; k++) pc.features[i][k] = feat[5 * i + k];
+            }
+        }
+        cvo::inn_p fip = odo.function_inner_product(&pcm, &pcf);
+        int inl2 = 0;
+        cvo::matrix66d_t H2 = odo.se3_Hessian(&pcm, &pcf, inl2);
+        printf("fip %.9g %d pre %.9g %d hess_inliers %d H2_00 %.9g\n", fip.value, fip.num, pre.value, pre.num, inl2, H2(0, 0));
+    }
     cvo::affine3f_t back = odo.reset_initial(tran);
     odo.update_fixed_pcd();
     odo.get_fixed_and_moving_number(nf, nm);

@@ -466,6 +466,9 @@ def test_cpp_dropin_matches_python_path(cuda_api, tum_calib, pair_c1, tmp_path):
     inn = [float(x) for x in lines["inn"][:4]]
     ref = [r["inn_pre"].value, r["inn_post"].value, r["inn_fixed_pcd"].value, r["inn_moving_pcd"].value]
     assert np.allclose(inn, ref, rtol=1e-6)
+    fip = [l.split() for l in out.splitlines() if l.startswith("fip ")][0]
+    assert float(fip[1]) == pytest.approx(float(fip[4]), rel=1e-6) and fip[2] == fip[5]   # wrapper == slot path
+    assert int(fip[7]) == int(fip[2])                                                  # same pair set
     assert "after update_fixed_pcd N %d 0" % c.get_fixed_and_moving_number()[1] in out
     c.close()
 
