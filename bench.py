@@ -299,6 +299,8 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     s1 = bt.stats()
+    ph = bt.phase_cycles()   # cumulative since creation: only the split is used
+    print("phase cycles (cumulative):", ph, "stats", s1, file=sys.stderr)
 
     # ---- end to end: host (pinned) images through the C ABI ------------------------------------------
     bgr_h = torch.empty(bgr_d.shape, dtype=torch.uint8, pin_memory=True).copy_(bgr_d)
@@ -363,7 +365,9 @@ def main():
                     evals_per_launch=evals, evals_per_s=evals / (align_ms * 1e-3),
                     eval_roofline_per_s=min(fp32_peak * 1e12 / FLOP_PER_EVAL,
                                             SM_COUNT * MUFU_LANES * sm_mhz * 1e6 / 2),
-                    iterations_per_pair=iters / n_pairs, nnz_per_iteration=nnz_it / max(iters, 1))
+                    iterations_per_pair=iters / n_pairs, nnz_per_iteration=nnz_it / max(iters, 1),
+                    phase_share={k: round(v / max(1, sum(v2 for k2, v2 in ph.items() if k2 != "rebuilds")), 4)
+                                 for k, v in ph.items() if k != "rebuilds"})
     line = dict(metric="cvo_frame_pair_alignments_per_s", value=value, unit="alignments/s", n_gpus=world,
                 steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32 (f64 exp)" if a.exp_mode == 0 else "f32", data="synthetic",

@@ -93,6 +93,14 @@ class Batch:
         self.api._check(self.lib.cvo_batch_stats(self.b, s), "batch_stats")
         return dict(launches=s[0], evals=s[1], iterations=s[2], nnz=s[3])
 
+    def phase_cycles(self):
+        """cumulative SM cycles (thread 0 of every CTA) per phase of the align kernel, and list rebuilds"""
+        s = (C.c_int64 * 8)()
+        self.lib.cvo_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        self.api._check(self.lib.cvo_batch_phase_cycles(self.b, s), "batch_phase_cycles")
+        names = ["grid", "P0", "P1a_search", "P1b", "P2", "P3", "P1a_retest", "rebuilds"]
+        return {k: int(s[i]) for i, k in enumerate(names)}
+
     def mark(self, which):
         self.api._check(self.lib.cvo_batch_mark(self.b, which), "batch_mark")
 

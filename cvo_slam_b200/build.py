@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libcvo_b200.so")
+OUT = os.environ.get("CVO_B200_OUT") or os.path.join(HERE, "libcvo_b200.so")
 # align.cu is compiled with -fmad=false: every float/double operation of the alignment loop must
 # round exactly as the oracle's (no FMA contraction); its hot loops use explicit _rn intrinsics.
 SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": []}
@@ -31,7 +31,7 @@ def build(force=False, verbose=False, extra=()):
     env = dict(os.environ)
     env.pop("CXX", None)   # the image exports a wrapper compiler; let nvcc use the system g++
     env.pop("CC", None)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.environ.get("CVO_B200_OBJDIR") or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []
     for src, flags in SOURCES.items():

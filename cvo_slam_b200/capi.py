@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcvo_b200.so")
+LIB_PATH = os.environ.get("CVO_B200_LIB") or os.path.join(HERE, "libcvo_b200.so")   # override: kernel-variant experiments only
 
 SLOT_FIXED, SLOT_MOVING, SLOT_PREVIOUS = 0, 1, 2
 
