@@ -98,7 +98,7 @@ class Batch:
         s = (C.c_int64 * 8)()
         self.lib.cvo_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         self.api._check(self.lib.cvo_batch_phase_cycles(self.b, s), "batch_phase_cycles")
-        names = ["grid", "P0", "P1a_search", "P1b", "P2", "P3", "P1a_retest", "rebuilds"]
+        names = ["grid", "P0", "P1a_search", "P1b", "P2", "P3", "P1a_ck", "rebuilds"]
         return {k: int(s[i]) for i, k in enumerate(names)}
 
     def mark(self, which):
