@@ -88,6 +88,22 @@ class Batch:
                         "batch_inner_product")
         return vals, nums
 
+    def verify_lc(self, pairs, results, prior_tran, lc_prior_tran, lc_prior_tran_2):
+        """compute_innerproduct_lc (cvo.cpp:505-561) + the accept rule of keyframe_graph.cpp:711-712 for
+        every pair in one launch; the three priors are [n,4,4] float32, lc_tran is results.transform.
+        -> structured array of capi.LC_DTYPE"""
+        d = pairs if isinstance(pairs, np.ndarray) and pairs.dtype == capi.PAIR_DTYPE \
+            else self.make_pairs(pairs)
+        n = len(d)
+        res = np.ascontiguousarray(results)
+        pr = [np.ascontiguousarray(np.asarray(m, np.float32).reshape(n, 16)) for m in
+              (prior_tran, lc_prior_tran, lc_prior_tran_2)]
+        out = np.zeros(n, dtype=capi.LC_DTYPE)
+        self.api._check(self.lib.cvo_batch_verify_lc(self.b, n, d.ctypes.data, res.ctypes.data, pr[0].ctypes.data,
+                                                     pr[1].ctypes.data, pr[2].ctypes.data, out.ctypes.data),
+                        "batch_verify_lc")
+        return out
+
     def stats(self):
         s = (C.c_int64 * 4)()
         self.api._check(self.lib.cvo_batch_stats(self.b, s), "batch_stats")

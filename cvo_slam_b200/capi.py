@@ -83,6 +83,18 @@ class PairDesc(C.Structure):
                 ("T", C.c_float * 3), ("ell", C.c_float)]
 
 
+class LcResult(C.Structure):
+    """cvo_lc_result (include/cvo_b200.h): compute_innerproduct_lc outputs + the caller's accept rule"""
+    _fields_ = [("value", C.c_float * 6), ("num", C.c_int32 * 6), ("post_hessian", C.c_double * 36),
+                ("inliers_svd", C.c_int32), ("inliers_pnpransac", C.c_int32), ("cos_angle", C.c_float),
+                ("accept", C.c_int32)]
+
+
+LC_NAMES = ("inn_prior", "inn_lc_prior", "inn_lc_pre", "inn_lc_post", "inn_fixed_pcd", "inn_moving_pcd")
+LC_DTYPE = np.dtype([("value", "<f4", (6,)), ("num", "<i4", (6,)), ("post_hessian", "<f8", (36,)),
+                     ("inliers_svd", "<i4"), ("inliers_pnpransac", "<i4"), ("cos_angle", "<f4"),
+                     ("accept", "<i4")])
+assert LC_DTYPE.itemsize == C.sizeof(LcResult)
 PAIR_DTYPE = np.dtype([("fixed_frame", "<i4"), ("moving_frame", "<i4"), ("R", "<f4", (9,)),
                        ("T", "<f4", (3,)), ("ell", "<f4")])
 RESULT_DTYPE = np.dtype([("transform", "<f4", (16,)), ("R", "<f4", (9,)), ("T", "<f4", (3,)),
@@ -308,6 +320,8 @@ class CudaLowLevel(LowLevel):
         lib.cvo_batch_align.argtypes = [vp, C.c_int, vp, vp]
         lib.cvo_batch_inner_product.argtypes = [vp, C.c_int, vp, vp, vp, vp]
         lib.cvo_batch_stats.argtypes = [vp, P(C.c_int64)]
+        lib.cvo_batch_verify_lc.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+        lib.cvo_compute_innerproduct_lc.argtypes = [vp, vp, vp, vp, vp, P(LcResult)]
         lib.cvo_batch_last_align_ms.argtypes = [vp, P(C.c_float)]
         lib.cvo_batch_mark.argtypes = [vp, C.c_int]
         lib.cvo_batch_elapsed_ms.argtypes = [vp, P(C.c_float)]
@@ -352,6 +366,14 @@ class CudaLowLevel(LowLevel):
                                                       H.ctypes.data_as(C.POINTER(C.c_double)), C.byref(inl)),
                     "compute_innerproduct")
         return [(float(v[k]), int(n[k])) for k in range(4)], H.reshape(6, 6), inl.value
+
+    def compute_innerproduct_lc(self, h, prior_tran, lc_prior_tran, lc_prior_tran_2, lc_tran):
+        """cvo_compute_innerproduct_lc: the eight queries of cvo.cpp:505-561 in one launch -> LcResult"""
+        Ts = [_f32(m, (16,)) for m in (prior_tran, lc_prior_tran, lc_prior_tran_2, lc_tran)]
+        out = LcResult()
+        self._check(self.lib.cvo_compute_innerproduct_lc(h, Ts[0].ctypes.data, Ts[1].ctypes.data, Ts[2].ctypes.data,
+                                                         Ts[3].ctypes.data, C.byref(out)), "compute_innerproduct_lc")
+        return out
 
     def handle_stats(self, h):
         s = (C.c_int64 * 4)()

@@ -11,6 +11,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <utility>
 #include <vector>
 
 namespace cvo_b200 {
@@ -93,6 +95,9 @@ struct cvo_batch {
     cvo_align_result *h_results = nullptr; // pinned
     QueryTask *h_q = nullptr;
     QueryOut *h_qo = nullptr;
+    QueryTask *d_lcq = nullptr;           // loop-closure verification queries (grown on demand)
+    QueryOut *d_lcqo = nullptr, *h_lcqo = nullptr;
+    int lc_cap = 0;
     int64_t launches = 0;
     float last_align_ms = 0.f;
 };
@@ -500,6 +505,54 @@ int cvo_compute_innerproduct(cvo_handle *h, const float tran[16], float values[4
     return CVO_OK;
 }
 
+// the accept rule of the reference's only caller (src/keyframe_graph.cpp:711-712)
+static void finish_lc_record(cvo_lc_result *o) {
+    o->cos_angle = o->value[3] / (sqrtf(o->value[4]) * sqrtf(o->value[5]));
+    const bool reject = (o->value[3] <= o->value[2]) || (o->value[3] <= o->value[1]) ||
+                        (o->value[3] <= o->value[0]) || o->cos_angle < 0.1f;
+    o->accept = reject ? 0 : 1;
+}
+
+// cvo::compute_innerproduct_lc (cvo.cpp:505-561) in one launch: six inner products and two
+// Hessians are eight independent queries, one CTA each.
+int cvo_compute_innerproduct_lc(cvo_handle *h, const float prior_tran[16], const float lc_prior_tran[16],
+                                const float lc_prior_tran_2[16], const float lc_tran[16], cvo_lc_result *out) {
+    if (!h || !prior_tran || !lc_prior_tran || !lc_prior_tran_2 || !lc_tran || !out) return CVO_ERR_INVALID;
+    if (h->slot_idx[CVO_SLOT_FIXED] < 0 || h->slot_idx[CVO_SLOT_MOVING] < 0) return CVO_ERR_NOT_INIT;
+    CVO_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = handle_ensure_aws(h);
+    if (rc != CVO_OK) return rc;
+    QueryTask *hq = reinterpret_cast<QueryTask *>(h->pinned + 8192);
+    QueryOut *ho = reinterpret_cast<QueryOut *>(h->pinned + 16384);
+    static_assert(sizeof(QueryTask) * 8 <= 8192 && sizeof(QueryOut) * 8 <= kPinnedBytes - 16384, "pinned staging");
+    static const float I34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const CloudView fx = h->arena.view(h->slot_idx[CVO_SLOT_FIXED]), mv = h->arena.view(h->slot_idx[CVO_SLOT_MOVING]);
+    // {inn_prior, inn_lc_prior, inn_lc_pre, inn_lc_post, inn_fixed_pcd, inn_moving_pcd, post_hessian, pnp-ransac Hessian}
+    const CloudView qa[8] = {mv, mv, mv, mv, fx, mv, mv, mv}, qb[8] = {fx, fx, fx, fx, fx, mv, fx, fx};
+    const float *qt[8] = {prior_tran, lc_prior_tran, I34, lc_tran, I34, I34, lc_tran, lc_prior_tran_2};
+    for (int k = 0; k < 8; k++) {
+        hq[k].a = qa[k];
+        hq[k].b = qb[k];
+        memcpy(hq[k].Ta, qt[k], sizeof(hq[k].Ta));
+        hq[k].ell = h->ell;
+        hq[k].kind = k >= 6 ? 1 : 0;
+    }
+    CVO_CUDA_TRY(cudaMemcpyAsync(h->d_q, hq, sizeof(QueryTask) * 8, cudaMemcpyHostToDevice, h->stream));
+    rc = query_run(h->aws, h->prm, 8, h->d_q, h->d_qo, h->stream, &h->launches);
+    if (rc != CVO_OK) return rc;
+    CVO_CUDA_TRY(cudaMemcpyAsync(ho, h->d_qo, sizeof(QueryOut) * 8, cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 6; k++) {
+        out->value[k] = (float)ho[k].sum;
+        out->num[k] = ho[k].count == 0 ? 1 : ho[k].count;
+    }
+    out->inliers_svd = ho[6].count;
+    finish_hessian_host(ho[6], out->post_hessian);
+    out->inliers_pnpransac = ho[7].count;
+    finish_lc_record(out);
+    return CVO_OK;
+}
+
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n) {
     if (!h || !slot_ok(slot) || !n) return CVO_ERR_INVALID;
     int m = 0;
@@ -616,6 +669,8 @@ int cvo_batch_destroy(cvo_batch *b) {
     align_ws_destroy(b->aws);
     if (b->arena.pos) arena_free(b->arena);
     cudaFree(b->d_tasks); cudaFree(b->d_results); cudaFree(b->d_q); cudaFree(b->d_qo);
+    cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
+    if (b->h_lcqo) cudaFreeHost(b->h_lcqo);
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
     if (b->h_results) cudaFreeHost(b->h_results);
     if (b->h_q) cudaFreeHost(b->h_q);
@@ -729,6 +784,91 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
     for (int i = 0; i < n_pairs; i++) {
         values[i] = (float)b->h_qo[i].sum;
         nums[i] = b->h_qo[i].count == 0 ? 1 : b->h_qo[i].count;
+    }
+    return CVO_OK;
+}
+
+// compute_innerproduct_lc for every pair of a batch: per pair four inner products and two Hessians
+// against the fixed frame, plus the self inner products once per distinct (frame, ell); one launch.
+int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, const cvo_align_result *results,
+                        const float *prior_tran, const float *lc_prior_tran, const float *lc_prior_tran_2,
+                        cvo_lc_result *out) {
+    if (!b || !pairs || !results || !prior_tran || !lc_prior_tran || !lc_prior_tran_2 || !out || n_pairs < 0 ||
+        n_pairs > b->max_pairs)
+        return CVO_ERR_INVALID;
+    if (n_pairs == 0) return CVO_OK;
+    for (int i = 0; i < n_pairs; i++)
+        if (pairs[i].fixed_frame < 0 || pairs[i].fixed_frame >= b->max_frames || pairs[i].moving_frame < 0 ||
+            pairs[i].moving_frame >= b->max_frames)
+            return CVO_ERR_INVALID;
+    CVO_CUDA_TRY(cudaSetDevice(b->device));
+    static const float I34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    // task list: 6 per pair, then one self inner product per distinct (frame, ell bits)
+    std::vector<QueryTask> q((size_t)n_pairs * 6);
+    std::map<std::pair<int, uint32_t>, int> self_of;
+    std::vector<int> self_fx(n_pairs), self_mv(n_pairs);
+    auto self_task = [&](int frame, float ell) {
+        uint32_t bits;
+        memcpy(&bits, &ell, 4);
+        auto key = std::make_pair(frame, bits);
+        auto it = self_of.find(key);
+        if (it != self_of.end()) return it->second;
+        QueryTask t;
+        t.a = b->arena.view(frame);
+        t.b = t.a;
+        memcpy(t.Ta, I34, sizeof(t.Ta));
+        t.ell = ell;
+        t.kind = 0;
+        q.push_back(t);
+        const int idx = (int)q.size() - 1;
+        self_of[key] = idx;
+        return idx;
+    };
+    for (int i = 0; i < n_pairs; i++) {
+        const CloudView fx = b->arena.view(pairs[i].fixed_frame), mv = b->arena.view(pairs[i].moving_frame);
+        const float *qt[6] = {prior_tran + 16 * (size_t)i, lc_prior_tran + 16 * (size_t)i, I34, results[i].transform,
+                              results[i].transform, lc_prior_tran_2 + 16 * (size_t)i};
+        for (int k = 0; k < 6; k++) {
+            QueryTask &t = q[(size_t)i * 6 + k];
+            t.a = mv;
+            t.b = fx;
+            memcpy(t.Ta, qt[k], sizeof(t.Ta));
+            t.ell = results[i].ell;
+            t.kind = k >= 4 ? 1 : 0;
+        }
+    }
+    for (int i = 0; i < n_pairs; i++) {
+        self_fx[i] = self_task(pairs[i].fixed_frame, results[i].ell);
+        self_mv[i] = self_task(pairs[i].moving_frame, results[i].ell);
+    }
+    const int nq = (int)q.size();
+    if (nq > b->lc_cap) {   // grow the device / pinned staging of the verification queries
+        cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
+        if (b->h_lcqo) cudaFreeHost(b->h_lcqo);
+        b->d_lcq = nullptr; b->d_lcqo = nullptr; b->h_lcqo = nullptr; b->lc_cap = 0;
+        const int cap = nq + nq / 4 + 64;
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lcq, sizeof(QueryTask) * cap));
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lcqo, sizeof(QueryOut) * cap));
+        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcqo, sizeof(QueryOut) * cap));
+        b->lc_cap = cap;
+    }
+    CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lcq, q.data(), sizeof(QueryTask) * nq, cudaMemcpyHostToDevice, b->stream));
+    int rc = query_run(b->aws, b->prm, nq, b->d_lcq, b->d_lcqo, b->stream, &b->launches);
+    if (rc != CVO_OK) return rc;
+    CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lcqo, b->d_lcqo, sizeof(QueryOut) * nq, cudaMemcpyDeviceToHost, b->stream));
+    CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < n_pairs; i++) {
+        const QueryOut *o = b->h_lcqo + (size_t)i * 6;
+        cvo_lc_result &r = out[i];
+        const QueryOut *src[6] = {o + 0, o + 1, o + 2, o + 3, b->h_lcqo + self_fx[i], b->h_lcqo + self_mv[i]};
+        for (int k = 0; k < 6; k++) {
+            r.value[k] = (float)src[k]->sum;
+            r.num[k] = src[k]->count == 0 ? 1 : src[k]->count;
+        }
+        r.inliers_svd = o[4].count;
+        finish_hessian_host(o[4], r.post_hessian);
+        r.inliers_pnpransac = o[5].count;
+        finish_lc_record(&r);
     }
     return CVO_OK;
 }

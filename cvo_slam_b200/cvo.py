@@ -122,6 +122,15 @@ class Cvo:
     def compute_innerproduct_lc(self, prior_tran, lc_prior_tran, lc_prior_tran_2, lc_tran):
         a = self.api
         f32 = lambda m: np.asarray(m, dtype=np.float32)  # noqa: E731
+        if hasattr(a, "compute_innerproduct_lc"):   # one launch for the eight queries (CUDA library)
+            r = a.compute_innerproduct_lc(self.h, f32(prior_tran), f32(lc_prior_tran), f32(lc_prior_tran_2),
+                                          f32(lc_tran))
+            inn = [InnP(float(r.value[k]), int(r.num[k])) for k in range(6)]
+            return dict(inn_prior=inn[0], inn_lc_prior=inn[1], inn_lc_pre=inn[2], inn_lc_post=inn[3],
+                        post_hessian=np.array(r.post_hessian[:], dtype=np.float64).reshape(6, 6),
+                        inliers_svd=int(r.inliers_svd), inliers_pnpransac=int(r.inliers_pnpransac),
+                        inn_fixed_pcd=inn[4], inn_moving_pcd=inn[5], cos_angle=np.float32(r.cos_angle),
+                        accept=bool(r.accept))
         inn_prior = InnP(*a.inner_product(self.h, SLOT_MOVING, f32(prior_tran), SLOT_FIXED))
         inn_lc_prior = InnP(*a.inner_product(self.h, SLOT_MOVING, f32(lc_prior_tran), SLOT_FIXED))
         inn_lc_pre = InnP(*a.inner_product(self.h, SLOT_MOVING, None, SLOT_FIXED))

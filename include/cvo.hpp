@@ -331,17 +331,18 @@ public:
         detail::to_rows(lc_prior_tran, Tlp);
         detail::to_rows(lc_prior_tran_2, Tlp2);
         detail::to_rows(lc_tran, Tl);
-        inn_prior.copy(inner(CVO_SLOT_MOVING, Tp, CVO_SLOT_FIXED));
-        inn_lc_prior.copy(inner(CVO_SLOT_MOVING, Tlp, CVO_SLOT_FIXED));
-        inn_lc_pre.copy(inner(CVO_SLOT_MOVING, nullptr, CVO_SLOT_FIXED));
-        inn_lc_post.copy(inner(CVO_SLOT_MOVING, Tl, CVO_SLOT_FIXED));
-        inn_fixed_pcd.copy(inner(CVO_SLOT_FIXED, nullptr, CVO_SLOT_FIXED));
-        inn_moving_pcd.copy(inner(CVO_SLOT_MOVING, nullptr, CVO_SLOT_MOVING));
+        cvo_lc_result r;   /* the six inner products and two Hessians in one launch */
+        check(cvo_compute_innerproduct_lc(h_, Tp, Tlp, Tlp2, Tl, &r), "cvo_compute_innerproduct_lc");
+        inn_prior.copy(inn_p(r.value[0], r.num[0], 0));
+        inn_lc_prior.copy(inn_p(r.value[1], r.num[1], 0));
+        inn_lc_pre.copy(inn_p(r.value[2], r.num[2], 0));
+        inn_lc_post.copy(inn_p(r.value[3], r.num[3], 0));
+        inn_fixed_pcd.copy(inn_p(r.value[4], r.num[4], 0));
+        inn_moving_pcd.copy(inn_p(r.value[5], r.num[5], 0));
         cos_angle = inn_lc_post.value / (std::sqrt(inn_fixed_pcd.value) * std::sqrt(inn_moving_pcd.value));
-        inliers_svd = 0;
-        post_hessian = hess(CVO_SLOT_MOVING, Tl, CVO_SLOT_FIXED, inliers_svd);
-        inliers_pnpransac = 0;
-        hess(CVO_SLOT_MOVING, Tlp2, CVO_SLOT_FIXED, inliers_pnpransac);
+        inliers_svd = r.inliers_svd;
+        inliers_pnpransac = r.inliers_pnpransac;
+        for (int a = 0; a < 6; a++) for (int c = 0; c < 6; c++) post_hessian(a, c) = r.post_hessian[a * 6 + c];
     }
 
     /* cvo.cpp:578-618: the unique_ptr moves become slot moves on the device clouds */

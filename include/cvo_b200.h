@@ -152,6 +152,27 @@ int cvo_hessian(cvo_handle *h, int slot_a, const float *Ta, int slot_b, double H
 int cvo_compute_innerproduct(cvo_handle *h, const float tran[16], float values[4], int nums[4],
                              double H[36], int *inliers);
 
+/* Loop-closure verification record: everything cvo::compute_innerproduct_lc (cvo.cpp:505-561)
+ * hands back for one candidate, plus the accept rule its only caller applies
+ * (src/keyframe_graph.cpp:711-712). */
+typedef struct cvo_lc_result {
+    /* {inn_prior, inn_lc_prior, inn_lc_pre, inn_lc_post, inn_fixed_pcd, inn_moving_pcd} */
+    float value[6];
+    int32_t num[6];
+    double post_hessian[36]; /* se3_Hessian(lc_tran * moving, fixed), eigenvalue-shifted   */
+    int32_t inliers_svd;     /* pairs of that Hessian                       (cvo.cpp:555) */
+    int32_t inliers_pnpransac; /* pairs under lc_prior_tran_2               (cvo.cpp:558) */
+    float cos_angle;         /* inn_lc_post / (sqrt(inn_fixed) sqrt(inn_moving))           */
+    int32_t accept;          /* inn_lc_post > {inn_lc_pre, inn_lc_prior, inn_prior} and cos_angle >= 0.1 */
+} cvo_lc_result;
+
+/* replaces the body of cvo::compute_innerproduct_lc (cvo.cpp:505-561) in one launch (the
+ * reference runs 6 KD-tree inner products and 2 Hessians one after the other).  All four
+ * transforms are 4x4 row-major and are applied to the moving cloud. */
+int cvo_compute_innerproduct_lc(cvo_handle *h, const float prior_tran[16], const float lc_prior_tran[16],
+                                const float lc_prior_tran_2[16], const float lc_tran[16],
+                                cvo_lc_result *out);
+
 /* replaces get_{fixed,moving}_frame_selected_points (cvo.hpp:275-276): xy pairs */
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n);
 /* positions n x 3, features n x 5 row-major (tests, and host point_cloud mirrors) */
@@ -186,6 +207,15 @@ int cvo_batch_align(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
 /* per-pair <T*moving, fixed> at each pair's final ell (compute_innerproduct_lc, cvo.cpp:545) */
 int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
                             const cvo_align_result *results, float *values, int *nums);
+/* compute_innerproduct_lc for every pair of a batch in one launch (the candidate loop of
+ * detectLoopClousure_top10, src/keyframe_graph.cpp:693-731, after cvo_batch_align):
+ * lc_tran = results[i].transform; prior / lc_prior / lc_prior_2 are n_pairs x 16 floats
+ * (4x4 row-major each).  The self inner products <fixed,fixed>, <moving,moving> are evaluated
+ * once per distinct (frame, ell). */
+int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
+                        const cvo_align_result *results, const float *prior_tran,
+                        const float *lc_prior_tran, const float *lc_prior_tran_2,
+                        cvo_lc_result *out);
 /* counters since creation: {kernel launches, in-cutoff kernel evaluations (d2 < d2_thres),
  * align iterations, stored non-zeros summed over iterations} */
 int cvo_batch_stats(cvo_batch *b, int64_t stats[4]);

@@ -592,3 +592,75 @@ def test_invalid_arguments_return_codes(cuda_api, tum_calib):
     with pytest.raises(CvoError):
         cuda_api.set_frame(h, 0, too_small, np.zeros((32, 32), np.uint16))
     cuda_api.destroy(h)
+
+
+def _perturbed(T, rot_deg, trans, seed):
+    """T composed with a small rigid perturbation (stand-ins for the PnP-RANSAC / SVD priors)."""
+    from cvo_slam_b200 import synth
+    rng = np.random.default_rng(seed)
+    P = synth.pose(rng.normal(0, np.deg2rad(rot_deg), 3), rng.normal(0, trans, 3)).astype(np.float32)
+    return (np.asarray(T, np.float32) @ P).astype(np.float32)
+
+
+@pytest.mark.gpu
+def test_compute_innerproduct_lc_fused_matches_oracle(cuda_api, oracle_api, tum_calib, pair_c1):
+    """cvo::compute_innerproduct_lc (cvo.cpp:505-561): the one-launch CUDA entry against the oracle's
+    eight separate queries, same transforms and ell on both sides; and the accept rule of
+    keyframe_graph.cpp:711-712."""
+    from cvo_slam_b200 import cvo as cvo_mod
+    bgr_a, d_a, bgr_b, d_b, T_gt = pair_c1
+    out = {}
+    for name, api in (("cuda", cuda_api), ("oracle", oracle_api)):
+        c = cvo_mod.Cvo(tum_calib, api=api)
+        c.set_pcd(bgr_a, d_a)
+        T = c.match_keyframe(bgr_b, d_b).astype(np.float32)
+        prior, lc_prior, lc_prior2 = _perturbed(T, 0.6, 8e-3, 1), _perturbed(T, 0.3, 4e-3, 2), _perturbed(T, 0.2, 3e-3, 3)
+        out[name] = (T, c.compute_innerproduct_lc(prior, lc_prior, lc_prior2, T))
+        c.close()
+    (Tc, rc), (To, ro) = out["cuda"], out["oracle"]
+    assert np.array_equal(Tc, To)   # bit-faithful alignment: identical transforms feed both sides
+    for k in ("inn_prior", "inn_lc_prior", "inn_lc_pre", "inn_lc_post", "inn_fixed_pcd", "inn_moving_pcd"):
+        assert rc[k].num == ro[k].num, k
+        assert rc[k].value == pytest.approx(ro[k].value, rel=INNER_RTOL), k
+    assert rc["inliers_svd"] == ro["inliers_svd"] and rc["inliers_pnpransac"] == ro["inliers_pnpransac"]
+    assert float(rc["cos_angle"]) == pytest.approx(float(ro["cos_angle"]), rel=1e-4)
+    Hc, Ho = rc["post_hessian"], ro["post_hessian"]
+    assert np.allclose(Hc, Ho, rtol=0, atol=1e-4 * np.abs(Ho).max())
+    # the aligned transform has the largest inner product: the candidate is accepted
+    assert rc["accept"] is True
+    assert rc["inn_lc_post"].value > max(rc["inn_lc_pre"].value, rc["inn_lc_prior"].value, rc["inn_prior"].value)
+
+
+@pytest.mark.gpu
+def test_batch_verify_lc_matches_handle_path(cuda_api, tum_calib):
+    """cvo_batch_verify_lc == per-pair cvo_compute_innerproduct_lc on a handle (same kernel, same
+    queries), including shared self inner products and a rejected candidate."""
+    from cvo_slam_b200 import batch as B, synth
+    scene = synth.make_scene(7)
+    rng = np.random.default_rng(7)
+    poses = [synth.pose()] + [synth.pose(rng.normal(0, 6e-3, 3), rng.normal(0, 8e-3, 3)) for _ in range(2)]
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=70 + k)) for k, P in enumerate(poses)]
+    pairs = [(0, 1), (0, 2), (1, 2), (2, 0)]
+    bt = B.Batch(tum_calib, max_frames=3, max_pairs=len(pairs), width=640, height=480)
+    bt.set_frames(np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]))
+    res = bt.align(pairs)
+    T = res["transform"].reshape(-1, 4, 4)
+    prior = np.stack([_perturbed(T[i], 0.6, 8e-3, 10 + i) for i in range(len(pairs))])
+    lc_prior = np.stack([_perturbed(T[i], 0.3, 4e-3, 20 + i) for i in range(len(pairs))])
+    lc_prior2 = np.stack([_perturbed(T[i], 0.2, 3e-3, 30 + i) for i in range(len(pairs))])
+    lc_prior[3] = T[3]   # a prior as good as the CVO result: inn_post <= inn_lc_prior -> reject
+    out = bt.verify_lc(pairs, res, prior, lc_prior, lc_prior2)
+    for i, (fi, mi) in enumerate(pairs):
+        h = cuda_api.create(tum_calib)
+        cuda_api.set_frame(h, 0, *frames[fi])
+        cuda_api.set_frame(h, 1, *frames[mi])
+        cuda_api.set_ell(h, float(res[i]["ell"]))
+        r = cuda_api.compute_innerproduct_lc(h, prior[i], lc_prior[i], lc_prior2[i], T[i])
+        assert np.array_equal(np.array(r.value[:], np.float32), out[i]["value"]), i
+        assert list(r.num[:]) == list(out[i]["num"])
+        assert np.array_equal(np.array(r.post_hessian[:]), out[i]["post_hessian"])
+        assert (r.inliers_svd, r.inliers_pnpransac, r.accept) == (out[i]["inliers_svd"], out[i]["inliers_pnpransac"], out[i]["accept"])
+        assert r.cos_angle == out[i]["cos_angle"]
+        cuda_api.destroy(h)
+    assert list(out["accept"]) == [1, 1, 1, 0]
+    bt.close()
