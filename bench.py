@@ -381,6 +381,29 @@ def main():
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, 1, 0, dev)
         line["cpu_baseline"] = cb
+    if world == 1:
+        # side measurement: the rest of a loop-closure verification (cvo::compute_innerproduct_lc,
+        # cvo.cpp:505-561, + the accept test of keyframe_graph.cpp:711-712) for every pair of the step,
+        # one launch.  lc_prior = the prior the alignment started from; prior / lc_prior_2 = that prior
+        # under two small perturbations (stand-ins for the motion-model and PnP-RANSAC estimates).
+        Rt = np.tile(np.eye(4, dtype=np.float32), (n_pairs, 1, 1))
+        Rt[:, :3, :3] = R0.reshape(-1, 3, 3)
+        Rt[:, :3, 3] = T0
+        lc_prior = np.linalg.inv(Rt.astype(np.float64)).astype(np.float32)
+        rng = np.random.default_rng(seed + 7)
+        def jitter(scale):
+            d = np.tile(np.eye(4, dtype=np.float32), (n_pairs, 1, 1))
+            d[:, :3, 3] = rng.normal(0, scale, (n_pairs, 3))
+            return (lc_prior @ d).astype(np.float32)
+        prior, lc_prior2 = jitter(5e-3), jitter(2e-3)
+        bt.verify_lc(desc, res, prior, lc_prior, lc_prior2)
+        torch.cuda.synchronize()
+        v0 = time.perf_counter()
+        lc = bt.verify_lc(desc, res, prior, lc_prior, lc_prior2)
+        v_ms = (time.perf_counter() - v0) * 1e3
+        line["lc_verify"] = dict(workload="cvo_batch_verify_lc over the step's pairs (6 queries per pair + self products, host call incl. D2H)",
+                                 ms=v_ms, pairs_per_s=n_pairs / (v_ms * 1e-3), accepted_fraction=float(lc["accept"].mean()),
+                                 verified_candidates_per_s=n_pairs / ((ms_step + v_ms) * 1e-3))
     if world == 1 and a.sequence_frames >= 8:
         bt.close()
         line["sequence_c2"] = sequence_leg(a.sequence_frames, api, dev, 0 if a.no_cpu_baseline else 6)

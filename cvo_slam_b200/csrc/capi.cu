@@ -95,9 +95,10 @@ struct cvo_batch {
     cvo_align_result *h_results = nullptr; // pinned
     QueryTask *h_q = nullptr;
     QueryOut *h_qo = nullptr;
-    QueryTask *d_lcq = nullptr;           // loop-closure verification queries (grown on demand)
+    LcTask *d_lc = nullptr, *h_lc = nullptr;           // loop-closure verification staging (first use)
+    LcOut *d_lco = nullptr, *h_lco = nullptr;
+    QueryTask *d_lcq = nullptr, *h_lcq = nullptr;      // its self inner products
     QueryOut *d_lcqo = nullptr, *h_lcqo = nullptr;
-    int lc_cap = 0;
     int64_t launches = 0;
     float last_align_ms = 0.f;
 };
@@ -669,7 +670,10 @@ int cvo_batch_destroy(cvo_batch *b) {
     align_ws_destroy(b->aws);
     if (b->arena.pos) arena_free(b->arena);
     cudaFree(b->d_tasks); cudaFree(b->d_results); cudaFree(b->d_q); cudaFree(b->d_qo);
-    cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
+    cudaFree(b->d_lc); cudaFree(b->d_lco); cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
+    if (b->h_lc) cudaFreeHost(b->h_lc);
+    if (b->h_lco) cudaFreeHost(b->h_lco);
+    if (b->h_lcq) cudaFreeHost(b->h_lcq);
     if (b->h_lcqo) cudaFreeHost(b->h_lcqo);
     if (b->h_tasks) cudaFreeHost(b->h_tasks);
     if (b->h_results) cudaFreeHost(b->h_results);
@@ -788,8 +792,10 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
     return CVO_OK;
 }
 
-// compute_innerproduct_lc for every pair of a batch: per pair four inner products and two Hessians
-// against the fixed frame, plus the self inner products once per distinct (frame, ell); one launch.
+// compute_innerproduct_lc for every pair of a batch.  One k_verify_lc CTA per pair evaluates the
+// four inner products and two Hessians against the fixed frame on one grid and finishes the Hessian
+// on the device; the self inner products <fixed,fixed>, <moving,moving> run once per distinct
+// (frame, ell) through k_query on the same stream.
 int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, const cvo_align_result *results,
                         const float *prior_tran, const float *lc_prior_tran, const float *lc_prior_tran_2,
                         cvo_lc_result *out) {
@@ -803,71 +809,70 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, c
             return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
     static const float I34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    // task list: 6 per pair, then one self inner product per distinct (frame, ell bits)
-    std::vector<QueryTask> q((size_t)n_pairs * 6);
+    if (!b->d_lc) {   // staging sized for max_pairs, allocated at the first verification
+        const size_t np = (size_t)b->max_pairs;
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lc, sizeof(LcTask) * np));
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lco, sizeof(LcOut) * np));
+        CVO_CUDA_TRY(cudaMallocHost(&b->h_lc, sizeof(LcTask) * np));
+        CVO_CUDA_TRY(cudaMallocHost(&b->h_lco, sizeof(LcOut) * np));
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lcq, sizeof(QueryTask) * 2 * np));
+        CVO_CUDA_TRY(cudaMalloc(&b->d_lcqo, sizeof(QueryOut) * 2 * np));
+        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcq, sizeof(QueryTask) * 2 * np));
+        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcqo, sizeof(QueryOut) * 2 * np));
+    }
     std::map<std::pair<int, uint32_t>, int> self_of;
     std::vector<int> self_fx(n_pairs), self_mv(n_pairs);
+    int nq = 0;
     auto self_task = [&](int frame, float ell) {
         uint32_t bits;
         memcpy(&bits, &ell, 4);
         auto key = std::make_pair(frame, bits);
         auto it = self_of.find(key);
         if (it != self_of.end()) return it->second;
-        QueryTask t;
+        QueryTask &t = b->h_lcq[nq];
         t.a = b->arena.view(frame);
         t.b = t.a;
         memcpy(t.Ta, I34, sizeof(t.Ta));
         t.ell = ell;
         t.kind = 0;
-        q.push_back(t);
-        const int idx = (int)q.size() - 1;
-        self_of[key] = idx;
-        return idx;
+        self_of[key] = nq;
+        return nq++;
     };
     for (int i = 0; i < n_pairs; i++) {
-        const CloudView fx = b->arena.view(pairs[i].fixed_frame), mv = b->arena.view(pairs[i].moving_frame);
+        LcTask &t = b->h_lc[i];
+        t.a = b->arena.view(pairs[i].moving_frame);
+        t.b = b->arena.view(pairs[i].fixed_frame);
         const float *qt[6] = {prior_tran + 16 * (size_t)i, lc_prior_tran + 16 * (size_t)i, I34, results[i].transform,
                               results[i].transform, lc_prior_tran_2 + 16 * (size_t)i};
-        for (int k = 0; k < 6; k++) {
-            QueryTask &t = q[(size_t)i * 6 + k];
-            t.a = mv;
-            t.b = fx;
-            memcpy(t.Ta, qt[k], sizeof(t.Ta));
-            t.ell = results[i].ell;
-            t.kind = k >= 4 ? 1 : 0;
-        }
-    }
-    for (int i = 0; i < n_pairs; i++) {
+        for (int k = 0; k < 6; k++) memcpy(t.T[k], qt[k], sizeof(t.T[k]));
+        t.ell = results[i].ell;
         self_fx[i] = self_task(pairs[i].fixed_frame, results[i].ell);
         self_mv[i] = self_task(pairs[i].moving_frame, results[i].ell);
     }
-    const int nq = (int)q.size();
-    if (nq > b->lc_cap) {   // grow the device / pinned staging of the verification queries
-        cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
-        if (b->h_lcqo) cudaFreeHost(b->h_lcqo);
-        b->d_lcq = nullptr; b->d_lcqo = nullptr; b->h_lcqo = nullptr; b->lc_cap = 0;
-        const int cap = nq + nq / 4 + 64;
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lcq, sizeof(QueryTask) * cap));
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lcqo, sizeof(QueryOut) * cap));
-        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcqo, sizeof(QueryOut) * cap));
-        b->lc_cap = cap;
-    }
-    CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lcq, q.data(), sizeof(QueryTask) * nq, cudaMemcpyHostToDevice, b->stream));
-    int rc = query_run(b->aws, b->prm, nq, b->d_lcq, b->d_lcqo, b->stream, &b->launches);
+    CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lc, b->h_lc, sizeof(LcTask) * n_pairs, cudaMemcpyHostToDevice, b->stream));
+    CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lcq, b->h_lcq, sizeof(QueryTask) * nq, cudaMemcpyHostToDevice, b->stream));
+    int rc = lc_run(b->aws, b->prm, n_pairs, b->d_lc, b->d_lco, b->stream, &b->launches);
     if (rc != CVO_OK) return rc;
+    rc = query_run(b->aws, b->prm, nq, b->d_lcq, b->d_lcqo, b->stream, &b->launches);
+    if (rc != CVO_OK) return rc;
+    CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lco, b->d_lco, sizeof(LcOut) * n_pairs, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lcqo, b->d_lcqo, sizeof(QueryOut) * nq, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
     for (int i = 0; i < n_pairs; i++) {
-        const QueryOut *o = b->h_lcqo + (size_t)i * 6;
+        const LcOut &o = b->h_lco[i];
         cvo_lc_result &r = out[i];
-        const QueryOut *src[6] = {o + 0, o + 1, o + 2, o + 3, b->h_lcqo + self_fx[i], b->h_lcqo + self_mv[i]};
-        for (int k = 0; k < 6; k++) {
-            r.value[k] = (float)src[k]->sum;
-            r.num[k] = src[k]->count == 0 ? 1 : src[k]->count;
+        for (int k = 0; k < 4; k++) {
+            r.value[k] = (float)o.sum[k];
+            r.num[k] = o.count[k] == 0 ? 1 : o.count[k];
         }
-        r.inliers_svd = o[4].count;
-        finish_hessian_host(o[4], r.post_hessian);
-        r.inliers_pnpransac = o[5].count;
+        const QueryOut *self[2] = {b->h_lcqo + self_fx[i], b->h_lcqo + self_mv[i]};
+        for (int k = 0; k < 2; k++) {
+            r.value[4 + k] = (float)self[k]->sum;
+            r.num[4 + k] = self[k]->count == 0 ? 1 : self[k]->count;
+        }
+        r.inliers_svd = o.inliers[0];
+        memcpy(r.post_hessian, o.H, sizeof(r.post_hessian));
+        r.inliers_pnpransac = o.inliers[1];
         finish_lc_record(&r);
     }
     return CVO_OK;

@@ -123,4 +123,21 @@ int query_run(AlignWorkspace *ws, const cvo_params &prm, int n, const QueryTask 
 // host: cvo.cpp:726-758 on the accumulated (unscaled) Hessian
 void finish_hessian_host(const QueryOut &q, double H[36]);
 
+// compute_innerproduct_lc (cvo.cpp:505-561) for one pair: six queries <T_k a, b> that share the
+// grid over b.  k = 0..3 inner products (prior, lc_prior, identity, lc), k = 4, 5 Hessians (lc,
+// lc_prior_2); only the first Hessian's matrix is used (cvo.cpp:555,558).
+struct LcTask {
+    CloudView a, b;         // a = moving, b = fixed
+    float T[6][12];         // 3x4 row-major each
+    float ell;
+};
+struct LcOut {
+    double sum[4];
+    double H[36];           // post_hessian, scaled and eigenvalue-shifted (cvo.cpp:726-758)
+    int count[4];
+    int inliers[2];
+};
+int lc_run(AlignWorkspace *ws, const cvo_params &prm, int n, const LcTask *tasks_dev, LcOut *out_dev,
+           cudaStream_t stream, int64_t *launch_counter);
+
 }  // namespace cvo_b200
