@@ -202,13 +202,19 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
         b, d = synth.render(scene, P, cal, W, H, noise_seed=20 + k, device=device)
         frames.append(synth.to_numpy(b, d))
     cvo_mod.track_sequence(frames[:4], cal, api=api)            # warm-up (allocations, attributes)
-    t0 = time.perf_counter()
-    out = cvo_mod.track_sequence(frames, cal, api=api)
-    dt = time.perf_counter() - t0
+    # a latency chain timed from the host is sensitive to whatever else the host does: three passes
+    # over the sequence, the fastest is reported (all three are listed)
+    passes = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = cvo_mod.track_sequence(frames, cal, api=api)
+        passes.append(time.perf_counter() - t0)
+    dt = min(passes)
     err = [synth.pose_error(o["keyframe"], synth.relative_transform(poses[0], poses[k + 1])) for k, o in enumerate(out)]
     res = dict(workload=f"C2: {n_frames}-frame synthetic TUM-shaped sequence, LocalTracker call pattern, 1 GPU",
                frames_per_s=(n_frames - 1) / dt, alignments_per_s=(2 * (n_frames - 1) - 1) / dt,
                ms_per_frame=dt / (n_frames - 1) * 1e3,
+               ms_per_frame_passes=[round(x / (n_frames - 1) * 1e3, 3) for x in passes],
                max_keyframe_pose_error=dict(rad=float(max(e[0] for e in err)), m=float(max(e[1] for e in err))))
     if cpu_frames:
         from oracle import oracle
