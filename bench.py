@@ -188,6 +188,33 @@ def cpu_leg(pairs, poses, R0, T0, seed, n_pairs, steps, warmup, device):
                        f"radius search, OpenMP over points"), per_step * 1e3
 
 
+def committed_ncu_traffic(n_frames, partners, exp_mode):
+    """DRAM bytes (read + write) of one k_align_batch launch from the committed `ncu --set full` summary of
+    THIS workload (profiles/r01_align_batch_v8_full_8192pairs.txt: bench.py defaults), or None for any
+    other configuration — a number taken under the profiler is never scaled to another size."""
+    if (n_frames, partners, exp_mode) != (1024, 8, 0):
+        return None, None
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_align_batch_v8_full_8192pairs.txt")
+    try:
+        txt = open(path).read()
+    except OSError:
+        return None, None
+    import re
+    rd = re.search(r"dram__bytes_read\.sum \[Gbyte\] = ([0-9.]+)", txt)
+    wr = re.search(r"dram__bytes_write\.sum \[Gbyte\] = ([0-9.]+)", txt)
+    if not (rd and wr):
+        return None, None
+    return (float(rd.group(1)) + float(wr.group(1))) * 1e9, os.path.relpath(path, os.path.dirname(os.path.abspath(__file__)))
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6549.0, "fallback: 6549 GB/s (the pool's measured copy bandwidth at the time of writing)"
+
+
 def sequence_leg(n_frames, api, device, cpu_frames=6):
     """BASELINE configs[1]: a TUM-shaped sequence tracked frame by frame with the LocalTracker call
     pattern (two cvo objects, persistent R/T/ell; 2 set_pcd + 2 align + 2 compute_innerproduct per
@@ -362,9 +389,11 @@ def main():
     fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
     flops = evals * FLOP_PER_EVAL + nnz_it * FLOP_PER_NNZ_ITER
     achieved = flops / (align_ms * 1e-3) / 1e12
+    traffic, traffic_src = committed_ncu_traffic(n_frames, a.partners, a.exp_mode)
+    hbm_peak, hbm_src = measured_hbm_peak()
     roofline = dict(bound="fp32 (non-tensor; exact mode adds 2 fp64 exp per eval)" if a.exp_mode == 0 else "fp32+mufu",
                     kernel="k_align_batch", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
-                    frac=achieved / fp32_peak, traffic=None,
+                    frac=achieved / fp32_peak, traffic=traffic,
                     peak_source=f"derived: {SM_COUNT} SM x {FP32_LANES} lanes x 2 x observed SM clock {sm_mhz:.0f} MHz "
                                 f"(MEASURED_PEAKS.json has no fp32 figure)",
                     kernel_ms_per_launch=align_ms, kernel_share_of_step=align_ms / ms_step,
@@ -372,6 +401,13 @@ def main():
                     eval_roofline_per_s=min(fp32_peak * 1e12 / FLOP_PER_EVAL,
                                             SM_COUNT * MUFU_LANES * sm_mhz * 1e6 / 2),
                     iterations_per_pair=iters / n_pairs, nnz_per_iteration=nnz_it / max(iters, 1),
+                    traffic_unit="bytes of DRAM read + write per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                    traffic_source=traffic_src,
+                    hbm=None if traffic is None else dict(
+                        achieved=traffic / (align_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                        frac=traffic / (align_ms * 1e-3) / 1e9 / hbm_peak, peak_source=hbm_src,
+                        note="list scratch streamed per iteration (see DESIGN section 3), not algorithmic bytes: "
+                             "the clouds themselves are 0.2 MB per pair"),
                     phase_share={k: round(v / max(1, sum(v2 for k2, v2 in ph.items() if k2 != "rebuilds")), 4)
                                  for k, v in ph.items() if k != "rebuilds"})
     line = dict(metric="cvo_frame_pair_alignments_per_s", value=value, unit="alignments/s", n_gpus=world,

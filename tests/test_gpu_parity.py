@@ -664,3 +664,58 @@ def test_batch_verify_lc_matches_handle_path(cuda_api, tum_calib):
         cuda_api.destroy(h)
     assert list(out["accept"]) == [1, 1, 1, 0]
     bt.close()
+
+
+def test_batch_shape_properties_512_pairs(cuda_api, tum_calib):
+    """The bench's workload shape at 1/16 of its size (64 keyframes x 8 partners = 512 pairs, priors via
+    reset_initial), checked through properties that do not need the oracle: every pair converges to the
+    rendered ground truth, a second run is bit-identical (no result depends on the order in which
+    CTAs pull pairs or warps append list entries), the (moving, fixed) swap gives the inverse pose
+    within the convergence basin, and the handle path reproduces sampled pairs to the bit."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    from cvo_slam_b200 import batch as B
+    spec = importlib.util.spec_from_file_location("cvo_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n_frames, partners, seed = 64, 8, 1000
+    pairs = bench.pair_list(n_frames, partners)
+    poses = bench.keyframe_poses(n_frames, seed)
+    R0, T0, gts = bench.pair_priors(pairs, poses, seed)
+    bgr_d, dep_d = bench.render_frames(list(range(n_frames)), poses, seed, "cuda:0")
+    prm = cuda_api.default_params()
+    bt = B.Batch(tum_calib, prm, max_frames=n_frames, max_pairs=len(pairs), width=640, height=480)
+    bt.set_frames_ptr(bgr_d.data_ptr(), dep_d.data_ptr(), n_frames, device=True)
+    desc = bt.make_pairs(pairs, R0.reshape(-1, 3, 3), T0, prm.ell_init)
+    res = bt.align(desc)
+    assert (res["status"] == 0).all()
+    errs = np.array([pose_error(r["transform"].reshape(4, 4), gt) for r, gt in zip(res, gts)])
+    assert np.median(errs[:, 1]) < 2e-3 and errs[:, 0].max() < 2e-2 and errs[:, 1].max() < 2e-2, errs.max(axis=0)
+    res2 = bt.align(desc)
+    assert np.array_equal(res["transform"], res2["transform"]) and np.array_equal(res["iterations"], res2["iterations"])
+    # swapped roles, fresh prior = inverse of the original prior: the result is the inverse pose up to
+    # the basin size (the two problems are different discretisations of the same registration)
+    sw = [(m, f) for f, m in pairs[:64]]
+    Rt = np.tile(np.eye(4), (64, 1, 1))
+    Rt[:, :3, :3] = R0.reshape(-1, 3, 3)[:64]
+    Rt[:, :3, 3] = T0[:64]
+    Rti = np.linalg.inv(Rt)
+    res_sw = bt.align(bt.make_pairs(sw, Rti[:, :3, :3].astype(np.float32), Rti[:, :3, 3].astype(np.float32), prm.ell_init))
+    for r, rs in zip(res[:64], res_sw):
+        ang, dist = pose_error(np.linalg.inv(rs["transform"].reshape(4, 4).astype(np.float64)), r["transform"].reshape(4, 4))
+        assert ang < 1e-2 and dist < 1e-2, (ang, dist)
+    # handle path == batch path for sampled pairs (same kernel, cluster of CTAs instead of one CTA)
+    frames = [(bgr_d[k].cpu().numpy(), dep_d[k].cpu().numpy().view(np.uint16)) for k in range(n_frames)]
+    for k in (0, 137, 511):
+        f, m = pairs[k]
+        h = cuda_api.create(tum_calib, prm)
+        cuda_api.set_frame(h, 0, *frames[f])
+        cuda_api.set_frame(h, 1, *frames[m])
+        cuda_api.set_RT(h, R0.reshape(-1, 3, 3)[k], T0[k])
+        cuda_api.set_ell(h, prm.ell_init)
+        rs, _ = cuda_api.align(h)
+        assert np.array_equal(rs.transform_np().reshape(-1), res[k]["transform"]), k
+        assert rs.iterations == res[k]["iterations"]
+        cuda_api.destroy(h)
+    bt.close()
