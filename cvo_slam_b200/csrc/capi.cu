@@ -809,16 +809,27 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, c
             return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
     static const float I34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    if (!b->d_lc) {   // staging sized for max_pairs, allocated at the first verification
+    if (!b->d_lc) {   // staging sized for max_pairs, allocated at the first verification (all or nothing)
         const size_t np = (size_t)b->max_pairs;
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lc, sizeof(LcTask) * np));
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lco, sizeof(LcOut) * np));
-        CVO_CUDA_TRY(cudaMallocHost(&b->h_lc, sizeof(LcTask) * np));
-        CVO_CUDA_TRY(cudaMallocHost(&b->h_lco, sizeof(LcOut) * np));
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lcq, sizeof(QueryTask) * 2 * np));
-        CVO_CUDA_TRY(cudaMalloc(&b->d_lcqo, sizeof(QueryOut) * 2 * np));
-        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcq, sizeof(QueryTask) * 2 * np));
-        CVO_CUDA_TRY(cudaMallocHost(&b->h_lcqo, sizeof(QueryOut) * 2 * np));
+        cudaError_t e = cudaMalloc(&b->d_lc, sizeof(LcTask) * np);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_lco, sizeof(LcOut) * np);
+        if (e == cudaSuccess) e = cudaMallocHost(&b->h_lc, sizeof(LcTask) * np);
+        if (e == cudaSuccess) e = cudaMallocHost(&b->h_lco, sizeof(LcOut) * np);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_lcq, sizeof(QueryTask) * 2 * np);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_lcqo, sizeof(QueryOut) * 2 * np);
+        if (e == cudaSuccess) e = cudaMallocHost(&b->h_lcq, sizeof(QueryTask) * 2 * np);
+        if (e == cudaSuccess) e = cudaMallocHost(&b->h_lcqo, sizeof(QueryOut) * 2 * np);
+        if (e != cudaSuccess) {
+            cudaFree(b->d_lc); cudaFree(b->d_lco); cudaFree(b->d_lcq); cudaFree(b->d_lcqo);
+            if (b->h_lc) cudaFreeHost(b->h_lc);
+            if (b->h_lco) cudaFreeHost(b->h_lco);
+            if (b->h_lcq) cudaFreeHost(b->h_lcq);
+            if (b->h_lcqo) cudaFreeHost(b->h_lcqo);
+            b->d_lc = nullptr; b->d_lco = nullptr; b->d_lcq = nullptr; b->d_lcqo = nullptr;
+            b->h_lc = nullptr; b->h_lco = nullptr; b->h_lcq = nullptr; b->h_lcqo = nullptr;
+            set_last_error("cvo_batch_verify_lc: staging allocation failed: %s", cudaGetErrorString(e));
+            return CVO_ERR_CUDA;
+        }
     }
     std::map<std::pair<int, uint32_t>, int> self_of;
     std::vector<int> self_fx(n_pairs), self_mv(n_pairs);
