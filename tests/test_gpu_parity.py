@@ -591,6 +591,12 @@ def test_invalid_arguments_return_codes(cuda_api, tum_calib):
     too_small = np.zeros((32, 32, 3), np.uint8)
     with pytest.raises(CvoError):
         cuda_api.set_frame(h, 0, too_small, np.zeros((32, 32), np.uint16))
+    # loop-closure verification: clouds missing -> not initialised; null pointers -> invalid
+    I = np.eye(4, dtype=np.float32)
+    with pytest.raises(CvoError):
+        cuda_api.compute_innerproduct_lc(h, I, I, I, I)
+    assert lib.cvo_compute_innerproduct_lc(h, None, None, None, None, None) == -1
+    assert lib.cvo_batch_verify_lc(None, 1, None, None, None, None, None, None) == -1
     cuda_api.destroy(h)
 
 
