@@ -149,9 +149,8 @@ static int handle_ensure_aws(cvo_handle *h) {
     }
     if (h->aws && align_ws_max_points(h->aws) >= need) return CVO_OK;
     if (h->aws) { CVO_CUDA_TRY(cudaStreamSynchronize(h->stream)); align_ws_destroy(h->aws); h->aws = nullptr; }
-    // a handle aligns one pair at a time on one thread-block cluster: 8 CTAs, or 16 (the largest,
-    // non-portable size) once its clouds are large enough to feed them (dense selection, C3)
-    return align_ws_create(&h->aws, need, h->device, need > 8192 ? 16 : 8);
+    // a handle aligns one pair at a time on one thread-block cluster of up to 16 CTAs
+    return align_ws_create(&h->aws, need, h->device, 16);
 }
 
 static int handle_slot_arena_index(cvo_handle *h, int slot) {
