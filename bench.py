@@ -215,6 +215,38 @@ def measured_hbm_peak():
         return 6549.0, "fallback: 6549 GB/s (the pool's measured copy bandwidth at the time of writing)"
 
 
+def cpp_sequence(frames, T_kf_last_python):
+    """Compiles scripts/seq_dropin.cpp against include/cvo.hpp + libcvo_b200.so and runs it on `frames`
+    (list of (bgr, depth) arrays).  -> dict(ms_per_frame, passes, same_bits) or None."""
+    from cvo_slam_b200 import capi
+    root = os.path.dirname(os.path.abspath(__file__))
+    libdir = os.path.dirname(capi.LIB_PATH)
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            exe = os.path.join(td, "seq_dropin")
+            subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
+                            os.path.join(root, "scripts", "seq_dropin.cpp"), "-o", exe, "-L", libdir, "-lcvo_b200",
+                            f"-Wl,-rpath,{libdir}"], check=True, capture_output=True)
+            np.stack([f[0] for f in frames]).tofile(os.path.join(td, "bgr.raw"))
+            np.stack([f[1] for f in frames]).astype(np.uint16).tofile(os.path.join(td, "depth.raw"))
+            calib = os.path.join(td, "calib.yaml")
+            with open(calib, "w") as f:   # config/TUM1.yaml:8-20
+                f.write("%YAML:1.0\nCamera.fx: 517.306408\nCamera.fy: 516.469215\nCamera.cx: 318.643040\n"
+                        "Camera.cy: 255.313989\nDepthMapFactor: 5000.0\n")
+            out = subprocess.run([exe, calib, os.path.join(td, "bgr.raw"), os.path.join(td, "depth.raw"),
+                                  str(len(frames)), str(W), str(H), "3"], check=True, capture_output=True, text=True).stdout
+        tok = out.split()
+        i = tok.index("ms_per_frame")
+        j = tok.index("T_kf_last")
+        passes = [float(x) for x in tok[i + 1:j]]
+        T = np.array([float(x) for x in tok[j + 1:j + 17]], np.float32).reshape(4, 4)
+        return dict(ms_per_frame=min(passes), passes=[round(x, 3) for x in passes],
+                    same_bits=bool(np.array_equal(T, np.asarray(T_kf_last_python, np.float32))))
+    except Exception as e:   # no compiler on the box, or the runner failed: the Python leg stands
+        print("cpp_sequence unavailable:", repr(e)[:300], file=sys.stderr)
+        return None
+
+
 def sequence_leg(n_frames, api, device, cpu_frames=6):
     """BASELINE configs[1]: a TUM-shaped sequence tracked frame by frame with the LocalTracker call
     pattern (two cvo objects, persistent R/T/ell; 2 set_pcd + 2 align + 2 compute_innerproduct per
@@ -243,6 +275,20 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
                ms_per_frame=dt / (n_frames - 1) * 1e3,
                ms_per_frame_passes=[round(x / (n_frames - 1) * 1e3, 3) for x in passes],
                max_keyframe_pose_error=dict(rad=float(max(e[0] for e in err)), m=float(max(e[1] for e in err))))
+    # the same sequence through the product's own host side: the drop-in C++ class (include/cvo.hpp)
+    # driven by scripts/seq_dropin.cpp exactly like LocalTracker drives the reference's class.  No
+    # Python between the calls: this is the number a CVO-SLAM build linked against libcvo_b200.so sees.
+    cpp = cpp_sequence(frames, out[-1]["keyframe"])
+    if cpp:
+        res["python_harness_ms_per_frame"] = res["ms_per_frame"]
+        res["python_harness_ms_per_frame_passes"] = res.pop("ms_per_frame_passes")
+        res.update(host="C++ drop-in class include/cvo.hpp (scripts/seq_dropin.cpp), fastest of three passes",
+                   ms_per_frame=cpp["ms_per_frame"], ms_per_frame_passes=cpp["passes"],
+                   frames_per_s=1e3 / cpp["ms_per_frame"],
+                   alignments_per_s=(2 * (n_frames - 1) - 1) / ((n_frames - 1) * cpp["ms_per_frame"] * 1e-3),
+                   cpp_matches_python_bits=cpp["same_bits"])
+    else:
+        res["host"] = "Python ctypes mirror of the class (cvo_slam_b200/cvo.py); the C++ runner could not be built here"
     if cpu_frames:
         from oracle import oracle
         orc = oracle.load()

@@ -17,6 +17,44 @@ from . import capi
 from .capi import SLOT_FIXED, SLOT_MOVING, SLOT_PREVIOUS
 
 
+def _mul44_f32(a, b):
+    """4x4 product in float32, sum over k in order (include/cvo.hpp detail::mul44)."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    o = np.zeros((4, 4), np.float32)
+    for r in range(4):
+        for c in range(4):
+            s = np.float32(0)
+            for k in range(4):
+                s = np.float32(s + np.float32(a[r, k] * b[k, c]))
+            o[r, c] = s
+    return o
+
+
+def _inv_affine_f32(a):
+    """Eigen::Affine3f::inverse() restated in float32 (include/cvo.hpp detail::inv_affine): cofactor inverse of
+    the linear part, translation = -(inverse * t)."""
+    a = np.asarray(a, np.float32)
+    f = np.float32
+
+    def cof(i, j):
+        i1, i2, j1, j2 = (i + 1) % 3, (i + 2) % 3, (j + 1) % 3, (j + 2) % 3
+        return f(f(a[i1, j1] * a[i2, j2]) - f(a[i1, j2] * a[i2, j1]))
+
+    c00, c10, c20 = cof(0, 0), cof(1, 0), cof(2, 0)
+    det = f(f(f(c00 * a[0, 0]) + f(c10 * a[1, 0])) + f(c20 * a[2, 0]))
+    invdet = f(f(1.0) / det)
+    inv = np.zeros((3, 3), np.float32)
+    for r in range(3):
+        for c in range(3):
+            inv[r, c] = f(cof(c, r) * invdet)
+    o = np.eye(4, dtype=np.float32)
+    o[:3, :3] = inv
+    for r in range(3):
+        o[r, 3] = -f(f(f(inv[r, 0] * a[0, 3]) + f(inv[r, 1] * a[1, 3])) + f(inv[r, 2] * a[2, 3]))
+    return o
+
+
 class InnP:
     """cvo::inn_p (cvo.hpp:52-80)"""
 
@@ -166,10 +204,11 @@ class Cvo:
         self.transform = np.asarray(odometry, dtype=np.float32).copy()
 
     def reset_initial(self, odometry):
-        init = np.linalg.inv((self.transform @ np.asarray(odometry, dtype=np.float32)).astype(np.float32))
-        init = init.astype(np.float32)
+        # the same float operations, in the same order, as include/cvo.hpp (detail::mul44 / inv_affine):
+        # the alignment that starts from this prior is sensitive to its last bits
+        init = _inv_affine_f32(_mul44_f32(self.transform, np.asarray(odometry, dtype=np.float32)))
         self.api.set_RT(self.h, init[:3, :3], init[:3, 3])
-        return np.linalg.inv(init).astype(np.float32)
+        return _inv_affine_f32(init)
 
     # ---- getters (cvo.hpp:268-276) -------------------------------------------------------------
     def get_fixed_and_moving_number(self):

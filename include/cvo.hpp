@@ -132,10 +132,28 @@ inline void mul44(const float a[16], const float b[16], float o[16]) {
         o[r * 4 + c] = s;
     }
 }
-/* inverse of a rigid transform [R t; 0 1] */
-inline void inv_rigid(const float a[16], float o[16]) {
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) o[r * 4 + c] = a[c * 4 + r];
-    for (int r = 0; r < 3; r++) o[r * 4 + 3] = -(o[r * 4] * a[3] + o[r * 4 + 1] * a[7] + o[r * 4 + 2] * a[11]);
+/* Eigen::Affine3f::inverse() as the reference's reset_initial uses it (cvo.cpp:613-617): the general
+ * 3x3 inverse of the linear part from its cofactors (Eigen's compute_inverse_size3: determinant from
+ * the first column's cofactors, one reciprocal), translation = -(inverse * t).  Not the transpose:
+ * for a float rotation matrix the two differ in the last bits, and the alignment that starts from
+ * this prior is sensitive to them.  Every operation in float, in this order. */
+inline void inv_affine(const float a[16], float o[16]) {
+    auto m = [&](int r, int c) { return a[r * 4 + c]; };
+    auto cof = [&](int i, int j) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1);
+    };
+    const float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const float det = (c00 * m(0, 0) + c10 * m(1, 0)) + c20 * m(2, 0);
+    const float invdet = 1.0f / det;
+    float inv[9];
+    inv[0] = c00 * invdet; inv[1] = c10 * invdet; inv[2] = c20 * invdet;
+    inv[3] = cof(0, 1) * invdet; inv[4] = cof(1, 1) * invdet; inv[5] = cof(2, 1) * invdet;
+    inv[6] = cof(0, 2) * invdet; inv[7] = cof(1, 2) * invdet; inv[8] = cof(2, 2) * invdet;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) o[r * 4 + c] = inv[r * 3 + c];
+        o[r * 4 + 3] = -((inv[r * 3] * a[3] + inv[r * 3 + 1] * a[7]) + inv[r * 3 + 2] * a[11]);
+    }
     o[12] = o[13] = o[14] = 0.f;
     o[15] = 1.f;
 }
@@ -366,11 +384,11 @@ public:
         detail::to_rows(transform, a);
         detail::to_rows(odometry, b);
         detail::mul44(a, b, c);
-        detail::inv_rigid(c, init_m); /* init = (transform * odometry).inverse() */
+        detail::inv_affine(c, init_m); /* init = (transform * odometry).inverse() */
         float R[9], T[3];
         for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) R[r * 3 + k] = init_m[r * 4 + k]; T[r] = init_m[r * 4 + 3]; }
         cvo_set_RT(h_, R, T);
-        detail::inv_rigid(init_m, back);
+        detail::inv_affine(init_m, back);
         affine3f_t out = affine3f_t::Identity();
         detail::from_rows(back, out);
         return out;

@@ -725,3 +725,23 @@ def test_batch_shape_properties_512_pairs(cuda_api, tum_calib):
         assert rs.iterations == res[k]["iterations"]
         cuda_api.destroy(h)
     bt.close()
+
+
+def test_cpp_dropin_sequence_matches_python_mirror(cuda_api, tum_calib, tmp_path):
+    """LocalTracker's per-frame pattern (two cvo objects, reset_initial, keyframe tracking) through the
+    drop-in C++ class (scripts/seq_dropin.cpp over include/cvo.hpp) ends on the same bits as the Python
+    mirror of the class: the host logic of cvo.cpp:578-618 is the same arithmetic in both."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    spec = importlib.util.spec_from_file_location("cvo_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    scene = synth.make_scene(2)
+    poses = synth.trajectory(8, 2)
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=20 + k)) for k, P in enumerate(poses)]
+    out = cvo_mod.track_sequence(frames, tum_calib, api=cuda_api)
+    cpp = bench.cpp_sequence(frames, out[-1]["keyframe"])
+    assert cpp is not None, "g++ or the runner failed"
+    assert cpp["same_bits"]
