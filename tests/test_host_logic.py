@@ -167,3 +167,33 @@ def test_cpp_dropin_header_compiles_and_links(tmp_path):
                  "get_fixed_frame_selected_points", "get_moving_frame_selected_points",
                  "first_frame", "prev_transform", "accum_transform"):
         assert name in src, name
+
+
+def test_reset_initial_arithmetic_header_equals_python_mirror(tmp_path):
+    """cvo::reset_initial (cvo.cpp:611-618) is host arithmetic: (transform * odom).inverse().  The drop-in
+    header (detail::mul44, detail::inv_affine: Eigen's cofactor inverse restated in float) and the Python
+    mirror (_mul44_f32, _inv_affine_f32) must agree to the bit — the alignment that starts from this
+    prior amplifies last-bit differences — and both must be an inverse to float accuracy."""
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    exe = os.path.join(str(tmp_path), "host_math")
+    # the header only needs cvo_b200.h for declarations here: nothing from the library is called
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "host_math.cpp"), "-o", exe,
+                    "-Wl,--unresolved-symbols=ignore-all"], check=True)
+    rng = np.random.default_rng(12)
+    cases = []
+    for _ in range(64):
+        A = synth.pose(rng.normal(0, 0.3, 3), rng.normal(0, 0.5, 3)).astype(np.float32)
+        B = synth.pose(rng.normal(0, 0.05, 3), rng.normal(0, 0.05, 3)).astype(np.float32)
+        cases.append((A, B))
+    text = "\n".join(" ".join(repr(float(v)) for v in np.concatenate([A.reshape(-1), B.reshape(-1)])) for A, B in cases)
+    out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(cases)
+    for (A, B), line in zip(cases, out):
+        bits = np.array([int(x, 16) for x in line.split()], dtype=np.uint32).view(np.float32)
+        C_cpp, I_cpp = bits[:16].reshape(4, 4), bits[16:].reshape(4, 4)
+        C_py = cvo_mod._mul44_f32(A, B)
+        I_py = cvo_mod._inv_affine_f32(C_py)
+        assert np.array_equal(C_cpp.view(np.uint32), C_py.view(np.uint32))
+        assert np.array_equal(I_cpp.view(np.uint32), I_py.view(np.uint32))
+        assert np.abs(I_py.astype(np.float64) @ C_py.astype(np.float64) - np.eye(4)).max() < 5e-7
