@@ -149,7 +149,9 @@ static int handle_ensure_aws(cvo_handle *h) {
     }
     if (h->aws && align_ws_max_points(h->aws) >= need) return CVO_OK;
     if (h->aws) { CVO_CUDA_TRY(cudaStreamSynchronize(h->stream)); align_ws_destroy(h->aws); h->aws = nullptr; }
-    // a handle aligns one pair at a time on one thread-block cluster of up to 16 CTAs
+    // a handle aligns one pair at a time: on one thread-block cluster of up to 16 CTAs, or — for clouds
+    // large enough to feed them (dense selection, C3) — on a cooperative grid of 128 CTAs
+    if (need > 8192) return align_ws_create(&h->aws, need, h->device, 0, 128);
     return align_ws_create(&h->aws, need, h->device, 16);
 }
 

@@ -92,7 +92,7 @@ struct AlignTask {          // one frame pair
 struct AlignWorkspace;      // opaque scratch for `n_workgroups` concurrent pairs
 // max_workgroups > 0 bounds the number of resident CTAs the scratch is sized for (a handle only
 // ever runs one pair, i.e. one cluster); 0 = fill the GPU (batches)
-int align_ws_create(AlignWorkspace **ws, int max_points, int device, int max_workgroups);
+int align_ws_create(AlignWorkspace **ws, int max_points, int device, int max_workgroups, int coop_ctas = 0);
 void align_ws_destroy(AlignWorkspace *ws);
 int align_ws_max_points(const AlignWorkspace *ws);
 // Runs tasks[0..n) (device array) -> results[0..n) (device array).  trace may be null.
