@@ -197,3 +197,37 @@ def test_reset_initial_arithmetic_header_equals_python_mirror(tmp_path):
         assert np.array_equal(C_cpp.view(np.uint32), C_py.view(np.uint32))
         assert np.array_equal(I_cpp.view(np.uint32), I_py.view(np.uint32))
         assert np.abs(I_py.astype(np.float64) @ C_py.astype(np.float64) - np.eye(4)).max() < 5e-7
+
+
+def test_c_abi_struct_layouts_match_ctypes_mirrors(tmp_path):
+    """The structs that cross the C ABI by value (include/cvo_b200.h) have the size and field offsets the
+    ctypes / numpy mirrors in cvo_slam_b200/capi.py assume (a silent drift would corrupt results)."""
+    import ctypes as C
+    from cvo_slam_b200 import capi
+    src = os.path.join(str(tmp_path), "layout.c")
+    exe = os.path.join(str(tmp_path), "layout")
+    with open(src, "w") as f:
+        f.write('#include <stddef.h>\n#include <stdio.h>\n#include "cvo_b200.h"\n'
+                'int main(void) {\n'
+                '  printf("lc %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cvo_lc_result), offsetof(cvo_lc_result, num),'
+                ' offsetof(cvo_lc_result, post_hessian), offsetof(cvo_lc_result, inliers_svd),'
+                ' offsetof(cvo_lc_result, inliers_pnpransac), offsetof(cvo_lc_result, cos_angle), offsetof(cvo_lc_result, accept));\n'
+                '  printf("res %zu %zu %zu %zu %zu\\n", sizeof(cvo_align_result), offsetof(cvo_align_result, R),'
+                ' offsetof(cvo_align_result, T), offsetof(cvo_align_result, ell), offsetof(cvo_align_result, iterations));\n'
+                '  printf("pair %zu %zu %zu %zu\\n", sizeof(cvo_pair_desc), offsetof(cvo_pair_desc, R), offsetof(cvo_pair_desc, T),'
+                ' offsetof(cvo_pair_desc, ell));\n'
+                '  return 0;\n}\n')
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+    out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in
+               subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines())
+    L = capi.LcResult
+    assert out["lc"] == [C.sizeof(L), L.num.offset, L.post_hessian.offset, L.inliers_svd.offset,
+                         L.inliers_pnpransac.offset, L.cos_angle.offset, L.accept.offset]
+    assert capi.LC_DTYPE.itemsize == out["lc"][0]
+    assert [capi.LC_DTYPE.fields[k][1] for k in ("num", "post_hessian", "inliers_svd", "inliers_pnpransac", "cos_angle", "accept")] == out["lc"][1:]
+    R = capi.AlignResult
+    assert out["res"] == [C.sizeof(R), R.R.offset, R.T.offset, R.ell.offset, R.iterations.offset]
+    assert capi.RESULT_DTYPE.itemsize == out["res"][0]
+    P = capi.PairDesc
+    assert out["pair"] == [C.sizeof(P), P.R.offset, P.T.offset, P.ell.offset]
+    assert capi.PAIR_DTYPE.itemsize == out["pair"][0]
