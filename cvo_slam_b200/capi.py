@@ -375,6 +375,14 @@ class CudaLowLevel(LowLevel):
                                                          Ts[3].ctypes.data, C.byref(out)), "compute_innerproduct_lc")
         return out
 
+    def get_selected_points_device(self, h, slot):
+        """-> (device pointer as int, n): the selected pixels as n (x, y) float pairs on the device"""
+        ptr = C.c_void_p()
+        n = C.c_int(0)
+        self.lib.cvo_get_selected_points_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+        self._check(self.lib.cvo_get_selected_points_device(h, slot, C.byref(ptr), C.byref(n)), "get_selected_points_device")
+        return ptr.value, n.value
+
     def handle_stats(self, h):
         s = (C.c_int64 * 4)()
         self._check(self.lib.cvo_handle_stats(h, s), "handle_stats")

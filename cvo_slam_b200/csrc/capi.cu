@@ -573,6 +573,16 @@ int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n)
     return CVO_OK;
 }
 
+int cvo_get_selected_points_device(cvo_handle *h, int slot, const float **xy_dev, int *n) {
+    if (!h || !slot_ok(slot) || !xy_dev || !n) return CVO_ERR_INVALID;
+    int m = 0;
+    int rc = cvo_slot_size(h, slot, &m);   // synchronises the handle's stream
+    if (rc != CVO_OK) return rc;
+    *n = m;
+    *xy_dev = reinterpret_cast<const float *>(h->arena.pix + (size_t)h->slot_idx[slot] * h->arena.cap);
+    return CVO_OK;
+}
+
 int cvo_get_cloud(cvo_handle *h, int slot, float *positions, float *features, int cap, int *n) {
     if (!h || !slot_ok(slot) || !n) return CVO_ERR_INVALID;
     int m = 0;

@@ -175,6 +175,11 @@ int cvo_compute_innerproduct_lc(cvo_handle *h, const float prior_tran[16], const
 
 /* replaces get_{fixed,moving}_frame_selected_points (cvo.hpp:275-276): xy pairs */
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n);
+/* the same selected pixels without the round trip through host vectors (the
+ * ORB side filters its keypoints against them, src/ORBextractor.cpp:1114-1145): device pointer to
+ * n (x, y) float pairs in raster order, valid until the slot is overwritten or moved; work queued on
+ * the handle's stream has completed when the call returns. */
+int cvo_get_selected_points_device(cvo_handle *h, int slot, const float **xy_dev, int *n);
 /* positions n x 3, features n x 5 row-major (tests, and host point_cloud mirrors) */
 int cvo_get_cloud(cvo_handle *h, int slot, float *positions, float *features, int cap, int *n);
 /* selector internals for the bit-exactness tests: status map (w*h bytes, 0/1/2/4 after

@@ -745,3 +745,26 @@ def test_cpp_dropin_sequence_matches_python_mirror(cuda_api, tum_calib, tmp_path
     cpp = bench.cpp_sequence(frames, out[-1]["keyframe"])
     assert cpp is not None, "g++ or the runner failed"
     assert cpp["same_bits"]
+
+
+def test_selected_points_device_pointer(cuda_api, tum_calib, pair_c1):
+    """cvo_get_selected_points_device hands out the pixels the host getter copies (ORB-side consumer)."""
+    import torch
+    bgr_a, d_a, _, _, _ = pair_c1
+    h = cuda_api.create(tum_calib)
+    cuda_api.set_frame(h, 0, bgr_a, d_a)
+    host = cuda_api.get_selected_points(h, 0)
+    ptr, n = cuda_api.get_selected_points_device(h, 0)
+    assert n == len(host) and ptr
+    # read the device memory back through the CUDA runtime torch ships (same primary context)
+    import ctypes as C
+    import glob
+    import os
+    libs = sorted(glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")))
+    assert libs, "libcudart not found next to torch"
+    rt = C.CDLL(libs[0])
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    out = np.zeros((n, 2), np.float32)
+    assert rt.cudaMemcpy(out.ctypes.data, ptr, n * 8, 2) == 0   # cudaMemcpyDeviceToHost
+    assert np.array_equal(out, host)
+    cuda_api.destroy(h)
