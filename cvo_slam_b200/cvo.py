@@ -112,8 +112,10 @@ class Cvo:
         if res.iter >= 0:
             self.iter = res.iter          # `iter` is only written on break (cvo.cpp:783,805)
         self.A_nonzero = res.A_nonzero
-        self.prev_transform = self.transform.copy()
-        self.accum_transform = self.accum_transform @ self.transform
+        # cvo.cpp:815-816: `transform` as the last executed iteration's update_tf() left it
+        last = res.last_iter_transform_np()
+        self.prev_transform = last.copy()
+        self.accum_transform = _mul44_f32(self.accum_transform, last)
         self.transform = res.transform_np()
         return recs
 

@@ -260,11 +260,12 @@ public:
         if (rc != CVO_OK && rc != CVO_ERR_PAIR_OVERFLOW) return;
         if (r.iter >= 0) iter = r.iter; /* `iter` is written only on break (cvo.cpp:783,805) */
         A_nonzero = r.A_nonzero;
-        prev_transform = transform;
-        float a[16], b[16], c[16];
+        /* cvo.cpp:815-816: prev_transform / accum_transform take `transform` as the LAST executed
+         * iteration's update_tf() left it, not the final one */
+        detail::from_rows(r.last_iter_transform, prev_transform);
+        float a[16], c[16];
         detail::to_rows(accum_transform, a);
-        detail::to_rows(transform, b);
-        detail::mul44(a, b, c);
+        detail::mul44(a, r.last_iter_transform, c);
         detail::from_rows(c, accum_transform);
         detail::from_rows(r.transform, transform);
     }

@@ -991,9 +991,18 @@ struct OracleCvo {
             ell = (k > 9) ? prm.ell_after_k9 : ell;
             ell = (k > 19) ? prm.ell_after_k19 : ell;
         }
+        // cvo.cpp:815-816: prev_transform / accum_transform take `transform` as the last executed
+        // iteration's update_tf() left it, BEFORE the final update_tf()
+        float last_tf[16] = {0};
+        for (int i = 0; i < 3; i++) {
+            for (int j = 0; j < 3; j++) last_tf[i * 4 + j] = tf_lin.m[i][j];
+            last_tf[i * 4 + 3] = tf_tr[i];
+        }
+        last_tf[15] = 1.f;
         update_tf();
         if (out) {
             memset(out, 0, sizeof(*out));
+            memcpy(out->last_iter_transform, last_tf, sizeof(last_tf));
             for (int i = 0; i < 3; i++) {
                 for (int j = 0; j < 3; j++) { out->transform[i * 4 + j] = tf_lin.m[i][j]; out->R[i * 3 + j] = R.m[i][j]; }
                 out->transform[i * 4 + 3] = tf_tr[i];

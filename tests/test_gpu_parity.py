@@ -275,6 +275,9 @@ def test_align_parity_c1(cuda_api, oracle_api, tum_calib, pair_c1):
     assert rc.iterations == ro.iterations and rc.A_nonzero == ro.A_nonzero
     ang, dist = pose_error(rc.transform_np(), T_gt)
     assert ang < 5e-3 and dist < 5e-3
+    # prev_transform / accum_transform source (cvo.cpp:815-816): same bits as the oracle's
+    assert np.array_equal(rc.last_iter_transform_np(), ro.last_iter_transform_np())
+    assert not np.array_equal(rc.last_iter_transform_np(), rc.transform_np())
     # state persists: a second align of the same object starts from R, T, ell left behind
     assert cuda_api.get_ell(hc) == pytest.approx(oracle_api.get_ell(ho))
     Rc, Tc = cuda_api.get_RT(hc)

@@ -212,8 +212,9 @@ def test_c_abi_struct_layouts_match_ctypes_mirrors(tmp_path):
                 '  printf("lc %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cvo_lc_result), offsetof(cvo_lc_result, num),'
                 ' offsetof(cvo_lc_result, post_hessian), offsetof(cvo_lc_result, inliers_svd),'
                 ' offsetof(cvo_lc_result, inliers_pnpransac), offsetof(cvo_lc_result, cos_angle), offsetof(cvo_lc_result, accept));\n'
-                '  printf("res %zu %zu %zu %zu %zu\\n", sizeof(cvo_align_result), offsetof(cvo_align_result, R),'
-                ' offsetof(cvo_align_result, T), offsetof(cvo_align_result, ell), offsetof(cvo_align_result, iterations));\n'
+                '  printf("res %zu %zu %zu %zu %zu %zu\\n", sizeof(cvo_align_result), offsetof(cvo_align_result, R),'
+                ' offsetof(cvo_align_result, T), offsetof(cvo_align_result, ell), offsetof(cvo_align_result, iterations),'
+                ' offsetof(cvo_align_result, last_iter_transform));\n'
                 '  printf("pair %zu %zu %zu %zu\\n", sizeof(cvo_pair_desc), offsetof(cvo_pair_desc, R), offsetof(cvo_pair_desc, T),'
                 ' offsetof(cvo_pair_desc, ell));\n'
                 '  return 0;\n}\n')
@@ -226,8 +227,43 @@ def test_c_abi_struct_layouts_match_ctypes_mirrors(tmp_path):
     assert capi.LC_DTYPE.itemsize == out["lc"][0]
     assert [capi.LC_DTYPE.fields[k][1] for k in ("num", "post_hessian", "inliers_svd", "inliers_pnpransac", "cos_angle", "accept")] == out["lc"][1:]
     R = capi.AlignResult
-    assert out["res"] == [C.sizeof(R), R.R.offset, R.T.offset, R.ell.offset, R.iterations.offset]
+    assert out["res"] == [C.sizeof(R), R.R.offset, R.T.offset, R.ell.offset, R.iterations.offset,
+                          R.last_iter_transform.offset]
+    assert capi.RESULT_DTYPE.fields["last_iter_transform"][1] == R.last_iter_transform.offset
     assert capi.RESULT_DTYPE.itemsize == out["res"][0]
     P = capi.PairDesc
     assert out["pair"] == [C.sizeof(P), P.R.offset, P.T.offset, P.ell.offset]
     assert capi.PAIR_DTYPE.itemsize == out["pair"][0]
+
+
+def test_prev_and_accum_transform_follow_the_last_iteration(oracle_api):
+    """cvo.cpp:815-816: prev_transform / accum_transform take `transform` as update_tf() left it at the top
+    of the LAST executed iteration (the final update_tf() comes after).  Checked on the oracle: that matrix is
+    the final transform of the same alignment stopped one iteration earlier; and the Python mirror of the
+    class accumulates it (not the previous call's result)."""
+    from cvo_slam_b200 import capi, cvo as cvo_mod, synth
+    cal = capi.TUM1_CALIB()
+    a, da, b, db, _ = synth.make_pair(7, cal, rot_deg=0.8, trans=(0.015, -0.01, 0.012))
+    c = cvo_mod.Cvo(cal, api=oracle_api)
+    c.set_pcd(a, da)
+    c.match_odometry(b, db)
+    full = c.last_result
+    n = full.iterations
+    assert n > 3
+    p = oracle_api.default_params()
+    p.max_iter = n - 1
+    c2 = cvo_mod.Cvo(cal, p, api=oracle_api)
+    c2.set_pcd(a, da)
+    c2.match_odometry(b, db)
+    assert c2.last_result.iterations == n - 1
+    assert np.array_equal(full.last_iter_transform_np(), c2.last_result.transform_np())
+    assert not np.array_equal(full.last_iter_transform_np(), full.transform_np())
+    assert np.array_equal(c.prev_transform, full.last_iter_transform_np())
+    assert np.array_equal(c.accum_transform, full.last_iter_transform_np())   # identity * last
+    # a second align of the same object multiplies the new last-iteration transform in
+    c.set_pcd(b, db)
+    c.align()
+    want = cvo_mod._mul44_f32(full.last_iter_transform_np(), c.last_result.last_iter_transform_np())
+    assert np.array_equal(c.accum_transform, want)
+    c.close()
+    c2.close()
