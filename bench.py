@@ -5,9 +5,13 @@ Workload (BASELINE.json configs[4], the configuration the multi-GPU metric is qu
 the largest single-GPU configuration and the one that shards): F keyframes of one synthetic
 scene (TUM fr1 intrinsics), P = 8 F independent keyframe pairs with a perturbed prior
 (`reset_initial`), as in loop-closure verification (src/keyframe_graph.cpp:622-731).
-One *step* = point selection + features for all F frames, alignment of all P pairs, and the
-post-alignment inner product <T*moving, fixed> of every pair.  Weak scaling: every rank
-processes its own F frames / P pairs; `value` = pairs of all ranks / max-over-ranks step time.
+One *step* = point selection + features for the frames, alignment of the pairs, and the
+post-alignment inner product <T*moving, fixed> of every pair.  The job is ONE fixed list of P pairs
+over F frames (BASELINE configs[4]: "8192 independent keyframe-pair alignments sharded across
+1/2/4/8 B200"): with N ranks every rank takes a contiguous block of P/N pairs, selects only the
+frames that block touches, aligns, and the results are gathered on rank 0 — strong scaling, no
+collective on the data path.  `value` = P / max-over-ranks step time.  `--scaling weak` keeps the
+round-1 variant (every rank its own F frames / P pairs) and is reported as a side object at N > 1.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # CUDA path (libcvo_b200.so)
   python bench.py --impl reference ...                           # CPU reference arm (oracle)
@@ -52,6 +56,10 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=24, help="pairs in the bounded CPU sample")
     ap.add_argument("--exp-mode", type=int, default=0, help="0 exact (bit-faithful), 1 MUFU fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: one list of frames*partners pairs sharded over the ranks (default); "
+                         "weak: every rank its own list")
+    ap.add_argument("--side-legs", type=int, default=1, help="C1 / C3 / C4 single-pair legs and the fast-mode roofline (N=1 only)")
     ap.add_argument("--sequence-frames", type=int, default=300,
                     help="C2: frames of the sequential-tracking side measurement (N=1 only; 0 = skip)")
     return ap.parse_args()
@@ -316,23 +324,87 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
     return res
 
 
+def single_pair_legs(api, sm_mhz):
+    """Side legs at N = 1 (BASELINE configs[0], [2], [3]): one pair on one handle — C1 (640x480, 1 deg / 2.7 cm),
+    C3 (dense selection, ~18 k points) and C4 (739x458, 8 deg / 0.15 m, default and ell_init 0.25) — exact mode:
+    host-timed cvo_align (launch + D2H of the result), kernel evaluations per second and the FP32 fraction."""
+    from cvo_slam_b200 import capi, synth
+    fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6
+    eval_roof = min(fp32_peak / FLOP_PER_EVAL, SM_COUNT * MUFU_LANES * sm_mhz * 1e6 / 2)
+    out = {}
+
+    def leg(name, cal, a, da, b, db, params, reps, note):
+        h = api.create(cal, params)
+        api.set_frame(h, 0, a, da)
+        api.set_frame(h, 1, b, db)
+        n = (api.slot_size(h, 0), api.slot_size(h, 1))
+        best = None
+        for rep in range(reps + 1):   # first repetition = warm-up
+            api.set_RT(h, np.eye(3, dtype=np.float32), np.zeros(3, np.float32))
+            api.set_ell(h, params.ell_init)
+            s0 = api.handle_stats(h)
+            t0 = time.perf_counter()
+            res, _recs = api.align(h)
+            dt = time.perf_counter() - t0
+            s1 = api.handle_stats(h)
+            if rep and (best is None or dt < best[0]):
+                best = (dt, s1["evals"] - s0["evals"], s1["nnz"] - s0["nnz"], res.iterations, res.status)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            api.set_frame(h, 1, b, db)
+            api.slot_size(h, 1)
+        tsel = (time.perf_counter() - t0) / 3
+        api.destroy(h)
+        dt, ev, nnz, it, st = best
+        flops = ev * FLOP_PER_EVAL + nnz * FLOP_PER_NNZ_ITER
+        out[name] = dict(workload=note, points=list(n), iterations=it, status=st, align_ms=dt * 1e3,
+                         us_per_iteration=dt * 1e6 / max(it, 1), set_frame_ms=tsel * 1e3, evals=ev, nnz_sum=nnz,
+                         evals_per_s=ev / dt, frac_of_eval_roofline=ev / dt / eval_roof,
+                         tflops=flops / dt / 1e12, frac=flops / dt / fp32_peak)
+
+    tum = capi.TUM1_CALIB()
+    a, da, b, db, _ = synth.make_pair(1, tum)
+    leg("c1_single_pair", tum, a, da, b, db, api.default_params(), 5,
+        "C1: 640x480 pair, TUM fr1 intrinsics, 1 deg / 2.7 cm, defaults; handle path (cluster of 16 CTAs)")
+    a, da, b, db, _ = synth.make_pair(3, tum, high_gradient=True, rot_deg=0.8, trans=(0.015, -0.01, 0.012))
+    p = api.default_params()
+    p.num_want = 60000
+    leg("c3_dense_pair", tum, a, da, b, db, p, 3,
+        "C3: dense selection stress (num_want 60000 -> pot 1), one pair on a cooperative grid of 128 CTAs")
+    eth = capi.ETH3D_CALIB()
+    t = np.array([0.10, -0.05, 0.10])
+    t = t / np.linalg.norm(t) * 0.15
+    a, da, b, db, _ = synth.make_pair(4, eth, w=739, h=458, rot_deg=8.0, trans=tuple(t))
+    leg("c4_eth3d_pair", eth, a, da, b, db, api.default_params(), 2,
+        "C4: 739x458 pair, ETH3D intrinsics, 8 deg / 0.15 m, defaults (the schedule leaves the basin: ~740 iterations)")
+    p = api.default_params()
+    p.ell_init = 0.25
+    leg("c4_eth3d_pair_ell025", eth, a, da, b, db, p, 2, "C4 with ell_init = 0.25 (wide cutoff)")
+    return out
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_frames, n_pairs = a.frames, a.frames * a.partners
-    # weak scaling: every rank gets the same scene, keyframe poses and priors (statistically
-    # identical work per GPU); only the sensor noise of the rendered frames differs per rank
     seed = 1000
     poses = keyframe_poses(n_frames, seed)
     pairs = pair_list(n_frames, a.partners)
     R0, T0, gts = pair_priors(pairs, poses, seed)
-    config = dict(workload=f"C5 batch: {n_frames} synthetic 640x480 keyframes x {a.partners} partners = {n_pairs} "
-                           f"independent pairs per GPU (loop-closure verification shape), TUM fr1 intrinsics, "
-                           f"prior via reset_initial; step = select {n_frames} frames + align {n_pairs} pairs + inner products",
-                  frames_per_gpu=n_frames, pairs_per_gpu=n_pairs, exp_mode=a.exp_mode,
-                  l2="inputs per step (%.0f MB) exceed the 126 MB L2" % (n_frames * W * H * 5 / 1e6))
+    strong = a.scaling == "strong"
+    if strong:
+        wl = (f"C5 batch: ONE list of {n_pairs} independent pairs over {n_frames} synthetic 640x480 keyframes "
+              f"({a.partners} partners each, loop-closure verification shape), TUM fr1 intrinsics, prior via reset_initial, "
+              f"sharded over the ranks in contiguous blocks; step = select the block's frames + align its pairs + inner products")
+    else:
+        wl = (f"C5 batch: {n_frames} synthetic 640x480 keyframes x {a.partners} partners = {n_pairs} independent pairs "
+              f"per GPU (loop-closure verification shape), TUM fr1 intrinsics, prior via reset_initial; "
+              f"step = select {n_frames} frames + align {n_pairs} pairs + inner products")
+    config = dict(workload=wl, frames=n_frames, pairs=n_pairs, pairs_per_gpu=n_pairs // world if strong else n_pairs,
+                  exp_mode=a.exp_mode, sharding="contiguous blocks of pairs, no data-path collective, final gather" if strong else "replicas",
+                  l2="inputs per step (%.0f MB per GPU at N=1) exceed the 126 MB L2" % (n_frames * W * H * 5 / 1e6))
 
     if a.impl == "reference":
         if rank != 0:
@@ -341,7 +413,7 @@ def main():
         dev = "cuda:0" if torch.cuda.is_available() else "cpu"
         cb, ms = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, a.steps, a.warmup, dev, a.partners)
         line = dict(metric="cvo_frame_pair_alignments_per_s", value=cb["value"], unit="alignments/s", n_gpus=a.gpus,
-                    steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    steps=a.steps, warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling=a.scaling,
                     vs_baseline=None, dtype="f32 (f64 exp)", data="synthetic", config=config, impl="reference",
                     cpu_baseline=cb,
                     e2e=dict(value=cb["value"], unit="alignments/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -350,7 +422,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from cvo_slam_b200 import batch as B, capi
+    from cvo_slam_b200 import batch as B, capi, parallel
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
@@ -360,128 +432,195 @@ def main():
     cal = capi.TUM1_CALIB()
     prm = api.default_params()
     prm.exp_mode = a.exp_mode
-
-    bgr_d, dep_d = render_frames(list(range(n_frames)), poses, seed, dev, noise_salt=rank)
-    torch.cuda.synchronize()
-    bt = B.Batch(cal, prm, max_frames=n_frames, max_pairs=n_pairs, width=W, height=H, device=local_rank, api=api)
-    desc = bt.make_pairs(pairs, R0.reshape(-1, 3, 3), T0, prm.ell_init)
-
-    def step_device():
-        bt.mark(0)
-        bt.set_frames_ptr(bgr_d.data_ptr(), dep_d.data_ptr(), n_frames, device=True)
-        res = bt.align(desc)
-        vals, nums = bt.inner_product(desc, res)
-        bt.mark(1)
-        return res, vals, bt.elapsed_ms(), bt.last_align_ms()
+    pairs_np = np.asarray(pairs, dtype=np.int64)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        res, vals, _, _ = step_device()
-    s0 = bt.stats()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_dev, t_align = 0.0, 0.0
-    wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        res, vals, ms, ams = step_device()
-        t_dev += ms
-        t_align += ams
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
-    s1 = bt.stats()
-    ph = bt.phase_cycles()   # cumulative since creation: only the split is used
-    print("phase cycles (cumulative):", ph, "stats", s1, file=sys.stderr)
+    def run_arm(idx, noise_salt, steps, warmup, exp_mode, with_e2e=True, sample_clocks=False):
+        """Times `steps` steps over the pairs `idx` (global indices) on this rank -> dict of measurements."""
+        need = parallel.frames_needed(pairs_np, idx)
+        local = {int(f): k for k, f in enumerate(need)}
+        lp = [(local[int(f)], local[int(m)]) for f, m in pairs_np[idx]]
+        bgr_d, dep_d = render_frames([int(f) for f in need], poses, seed, dev, noise_salt=noise_salt)
+        torch.cuda.synchronize()
+        pr = api.default_params()
+        pr.exp_mode = exp_mode
+        bt = B.Batch(cal, pr, max_frames=len(need), max_pairs=max(1, len(idx)), width=W, height=H, device=local_rank, api=api)
+        desc = bt.make_pairs(lp, R0[idx].reshape(-1, 3, 3), T0[idx], pr.ell_init)
+        nf = len(need)
 
-    # ---- end to end: host (pinned) images through the C ABI ------------------------------------------
-    bgr_h = torch.empty(bgr_d.shape, dtype=torch.uint8, pin_memory=True).copy_(bgr_d)
-    dep_h = torch.empty(dep_d.shape, dtype=torch.int16, pin_memory=True).copy_(dep_d)
-    torch.cuda.synchronize()
+        def step_device():
+            bt.mark(0)
+            bt.set_frames_ptr(bgr_d.data_ptr(), dep_d.data_ptr(), nf, device=True)
+            res = bt.align(desc)
+            vals, nums = bt.inner_product(desc, res)
+            bt.mark(1)
+            return res, vals, bt.elapsed_ms(), bt.last_align_ms()
 
-    def step_host():
-        bt.set_frames_ptr(bgr_h.data_ptr(), dep_h.data_ptr(), n_frames, device=False)
-        r = bt.align(desc)
-        v, n = bt.inner_product(desc, r)
-        return r, v
+        for _ in range(warmup):
+            res, vals, _, _ = step_device()
+        s0 = bt.stats()
+        barrier()
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        t_dev = t_align = 0.0
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            res, vals, ms, ams = step_device()
+            t_dev += ms
+            t_align += ams
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        s1 = bt.stats()
+        out = dict(res=res, vals=vals, ms_step=t_dev / steps, align_ms=t_align / steps, wall_ms=wall / steps * 1e3,
+                   clocks=clocks, stats0=s0, stats1=s1, phases=bt.phase_cycles(), frames=nf, desc_bytes=desc.nbytes,
+                   idx=idx)
+        if with_e2e:
+            # end to end: host (pinned) images through the C ABI, H2D of every frame and D2H of every result inside the
+            # timed region; with N ranks the final gather of the results on rank 0 is inside as well
+            bgr_h = torch.empty(bgr_d.shape, dtype=torch.uint8, pin_memory=True).copy_(bgr_d)
+            dep_h = torch.empty(dep_d.shape, dtype=torch.int16, pin_memory=True).copy_(dep_d)
+            torch.cuda.synchronize()
+            per = (n_pairs + world - 1) // world
+            gbuf = torch.zeros(per * capi.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            glist = [torch.zeros_like(gbuf) for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    for _ in range(min(a.warmup, 2)):
-        step_host()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(a.steps):
-        res_h, vals_h = step_host()
-    barrier()
-    e2e_s = (time.perf_counter() - e0) / a.steps
+            def step_host():
+                bt.set_frames_ptr(bgr_h.data_ptr(), dep_h.data_ptr(), nf, device=False)
+                r = bt.align(desc)
+                v, n = bt.inner_product(desc, r)
+                if world > 1 and strong:
+                    raw = torch.from_numpy(r.view(np.uint8).reshape(-1))
+                    gbuf[:raw.numel()].copy_(raw, non_blocking=True)
+                    dist.gather(gbuf, glist, dst=0)
+                return r, v
 
-    # sanity inside the bench: results of the two legs agree, alignments converged to the truth
-    assert np.array_equal(res_h["transform"], res["transform"])
+            for _ in range(min(warmup, 2)):
+                step_host()
+            barrier()
+            e0 = time.perf_counter()
+            for _ in range(steps):
+                res_h, vals_h = step_host()
+            barrier()
+            out["e2e_s"] = (time.perf_counter() - e0) / steps
+            assert np.array_equal(res_h["transform"], res["transform"])   # the two legs agree to the bit
+            if glist is not None:   # rank 0: the gathered records, in pair order
+                full = np.zeros(n_pairs, dtype=capi.RESULT_DTYPE)
+                for r_, g in enumerate(glist):
+                    ir = parallel.partition_blocks(n_pairs, r_, world)
+                    full[ir] = np.frombuffer(g.cpu().numpy().tobytes()[:len(ir) * capi.RESULT_DTYPE.itemsize], dtype=capi.RESULT_DTYPE)
+                out["gathered"] = full
+        out["bt"] = bt
+        return out
+
+    idx = parallel.partition_blocks(n_pairs, rank, world) if strong else np.arange(n_pairs, dtype=np.int64)
+    m = run_arm(idx, 0 if strong else rank, a.steps, a.warmup, a.exp_mode, sample_clocks=True)
+    res, bt = m["res"], m["bt"]
+    print("phase cycles (cumulative):", m["phases"], "stats", m["stats1"], file=sys.stderr)
     err = []
-    for k in range(0, n_pairs, max(1, n_pairs // 64)):
-        E = np.linalg.inv(gts[k]) @ res["transform"][k].reshape(4, 4).astype(np.float64)
+    for k in range(0, len(idx), max(1, len(idx) // 64)):
+        E = np.linalg.inv(gts[int(idx[k])]) @ res["transform"][k].reshape(4, 4).astype(np.float64)
         err.append(np.linalg.norm(E[:3, 3]))
     status_bad = int((res["status"] != 0).sum())
 
-    ms_step = t_dev / a.steps
-    rank_ms = [ms_step]
+    # inside the run: the sharded job reproduces the single-GPU results to the bit.  Rank 0 re-aligns a sample of
+    # pairs from every rank's block on its own GPU (the full list at N = 1 IS the single-GPU run).
+    shard_check = None
+    if strong and world > 1 and rank == 0 and "gathered" in m:
+        samp = np.unique(np.linspace(0, n_pairs - 1, 128).astype(np.int64))
+        chk = run_arm(samp, 0, 1, 0, a.exp_mode, with_e2e=False)
+        same = bool(np.array_equal(chk["res"]["transform"], m["gathered"]["transform"][samp])
+                    and np.array_equal(chk["res"]["iterations"], m["gathered"]["iterations"][samp]))
+        chk["bt"].close()
+        shard_check = dict(pairs_rechecked_on_rank0=int(len(samp)), bit_identical=same)
+        assert same, "sharded results differ from the single-GPU results"
+
+    ms_step, e2e_s = m["ms_step"], m["e2e_s"]
+    rank_ms = [[round(ms_step, 2), round(m["align_ms"], 2), m["frames"], len(idx)]]
     if world > 1:
-        mine = torch.tensor([ms_step, t_align / a.steps], device=dev, dtype=torch.float64)
+        mine = torch.tensor([ms_step, m["align_ms"], m["frames"], len(idx)], device=dev, dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        rank_ms = [[round(float(x[0]), 2), round(float(x[1]), 2)] for x in allr]
+        rank_ms = [[round(float(x[0]), 2), round(float(x[1]), 2), int(x[2]), int(x[3])] for x in allr]
         t = torch.tensor([ms_step, e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_s = float(t[0]), float(t[1])
+
+    weak_side = None
+    if strong and world > 1:   # the round-1 variant beside it: every rank the full list (own sensor noise)
+        bt.close()
+        wk = run_arm(np.arange(n_pairs, dtype=np.int64), rank, 2, 1, a.exp_mode, with_e2e=False)
+        t = torch.tensor([wk["ms_step"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        weak_side = dict(scaling="weak", value=n_pairs * world / (float(t[0]) * 1e-3), unit="alignments/s",
+                         ms_per_step=float(t[0]), pairs_per_gpu=n_pairs, steps=2, warmup=1)
+        wk["bt"].close()
+        bt = None
     if rank != 0:
+        if bt is not None:
+            bt.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total_pairs = n_pairs * world
+    total_pairs = n_pairs if strong else n_pairs * world
     value = total_pairs / (ms_step * 1e-3)
+    s0, s1, clocks = m["stats0"], m["stats1"], m["clocks"]
+    my_pairs = len(idx)
     evals = (s1["evals"] - s0["evals"]) / a.steps
     nnz_it = (s1["nnz"] - s0["nnz"]) / a.steps
     iters = (s1["iterations"] - s0["iterations"]) / a.steps
     launches = (s1["launches"] - s0["launches"]) // a.steps
-    align_ms = t_align / a.steps
+    align_ms = m["align_ms"]
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
-    flops = evals * FLOP_PER_EVAL + nnz_it * FLOP_PER_NNZ_ITER
-    achieved = flops / (align_ms * 1e-3) / 1e12
-    traffic, traffic_src = committed_ncu_traffic(n_frames, a.partners, a.exp_mode)
-    hbm_peak, hbm_src = measured_hbm_peak()
-    roofline = dict(bound="fp32 (non-tensor; exact mode adds 2 fp64 exp per eval)" if a.exp_mode == 0 else "fp32+mufu",
+
+    def roofline_of(evals, nnz_it, iters, align_ms, ms_step, exp_mode, phases, pairs_here):
+        flops = evals * FLOP_PER_EVAL + nnz_it * FLOP_PER_NNZ_ITER
+        achieved = flops / (align_ms * 1e-3) / 1e12
+        traffic, traffic_src = committed_ncu_traffic(n_frames, a.partners, exp_mode) if pairs_here == n_pairs else (None, None)
+        hbm_peak, hbm_src = measured_hbm_peak()
+        return dict(bound="fp32 (non-tensor; exact mode adds 1 fp64 exp per eval and exact accumulation)" if exp_mode == 0 else "fp32+mufu",
                     kernel="k_align_batch", achieved=achieved, peak=fp32_peak, unit="TFLOP/s",
                     frac=achieved / fp32_peak, traffic=traffic,
                     peak_source=f"derived: {SM_COUNT} SM x {FP32_LANES} lanes x 2 x observed SM clock {sm_mhz:.0f} MHz "
                                 f"(MEASURED_PEAKS.json has no fp32 figure)",
-                    kernel_ms_per_launch=align_ms, kernel_share_of_step=align_ms / ms_step,
+                    kernel_ms_per_launch=align_ms, kernel_share_of_step=align_ms / ms_step, pairs_per_launch=pairs_here,
                     evals_per_launch=evals, evals_per_s=evals / (align_ms * 1e-3),
                     eval_roofline_per_s=min(fp32_peak * 1e12 / FLOP_PER_EVAL,
                                             SM_COUNT * MUFU_LANES * sm_mhz * 1e6 / 2),
-                    iterations_per_pair=iters / n_pairs, nnz_per_iteration=nnz_it / max(iters, 1),
+                    iterations_per_pair=iters / max(pairs_here, 1), nnz_per_iteration=nnz_it / max(iters, 1),
                     traffic_unit="bytes of DRAM read + write per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                     traffic_source=traffic_src,
                     hbm=None if traffic is None else dict(
                         achieved=traffic / (align_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
                         frac=traffic / (align_ms * 1e-3) / 1e9 / hbm_peak, peak_source=hbm_src,
-                        note="list scratch streamed per iteration (see DESIGN section 3), not algorithmic bytes: "
+                        note="neighbour / verdict lists streamed per iteration (see DESIGN section 3), not algorithmic bytes: "
                              "the clouds themselves are 0.2 MB per pair"),
-                    phase_share={k: round(v / max(1, sum(v2 for k2, v2 in ph.items() if k2 != "rebuilds")), 4)
-                                 for k, v in ph.items() if k != "rebuilds"})
+                    phase_share={k: round(v / max(1, sum(v2 for k2, v2 in phases.items() if k2 != "rebuilds")), 4)
+                                 for k, v in phases.items() if k != "rebuilds"})
+
+    roofline = roofline_of(evals, nnz_it, iters, align_ms, m["ms_step"], a.exp_mode, m["phases"], my_pairs)
+    if world > 1:
+        roofline["note"] = "rank 0's launch (its block of the list)"
     line = dict(metric="cvo_frame_pair_alignments_per_s", value=value, unit="alignments/s", n_gpus=world,
-                steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                steps=a.steps, warmup=a.warmup, ms_per_step=ms_step, higher_is_better=True, scaling=a.scaling,
                 vs_baseline=None, dtype="f32 (f64 exp)" if a.exp_mode == 0 else "f32", data="synthetic",
                 config=config, clocks=clocks,
                 e2e=dict(value=total_pairs / e2e_s, unit="alignments/s",
-                         h2d_bytes_per_step=int(n_frames * W * H * 5 + desc.nbytes * 2),
-                         d2h_bytes_per_step=int(res.nbytes + n_pairs * 192)),
+                         h2d_bytes_per_step=int(m["frames"] * W * H * 5 + m["desc_bytes"] * 2),
+                         d2h_bytes_per_step=int(res.nbytes + my_pairs * 192),
+                         note="bytes of rank 0; the timed region includes the gather of all results on rank 0" if world > 1 else None),
                 gpu_launches=int(launches * a.steps), roofline=roofline,
-                wall_ms_per_step=wall / a.steps * 1e3, per_rank_ms_step_and_align=rank_ms,
+                wall_ms_per_step=m["wall_ms"], per_rank_ms_step_align_frames_pairs=rank_ms,
                 check=dict(median_translation_error_m=float(np.median(err)), pairs_with_error_status=status_bad))
+    if shard_check:
+        line["shard_check"] = shard_check
+    if weak_side:
+        line["weak"] = weak_side
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_leg(pairs, poses, R0, T0, seed, a.cpu_pairs, 1, 0, dev, a.partners)
         line["cpu_baseline"] = cb
@@ -490,6 +629,7 @@ def main():
         # cvo.cpp:505-561, + the accept test of keyframe_graph.cpp:711-712) for every pair of the step,
         # one launch.  lc_prior = the prior the alignment started from; prior / lc_prior_2 = that prior
         # under two small perturbations (stand-ins for the motion-model and PnP-RANSAC estimates).
+        desc = bt.make_pairs(pairs, R0.reshape(-1, 3, 3), T0, prm.ell_init)
         Rt = np.tile(np.eye(4, dtype=np.float32), (n_pairs, 1, 1))
         Rt[:, :3, :3] = R0.reshape(-1, 3, 3)
         Rt[:, :3, 3] = T0
@@ -508,11 +648,22 @@ def main():
         line["lc_verify"] = dict(workload="cvo_batch_verify_lc over the step's pairs (6 queries per pair + self products, host call incl. D2H)",
                                  ms=v_ms, pairs_per_s=n_pairs / (v_ms * 1e-3), accepted_fraction=float(lc["accept"].mean()),
                                  verified_candidates_per_s=n_pairs / ((ms_step + v_ms) * 1e-3))
-    if world == 1 and a.sequence_frames >= 8:
+    if bt is not None:
         bt.close()
+    if world == 1 and a.side_legs:
+        # the FP32 + MUFU mode of the same launch (the kernel north_star's roofline is defined on), beside the exact headline
+        other = 1 - a.exp_mode if a.exp_mode in (0, 1) else 1
+        fm = run_arm(np.arange(n_pairs, dtype=np.int64), 0, 2, 2, other, with_e2e=False)
+        f0, f1 = fm["stats0"], fm["stats1"]
+        key = "roofline_fast" if other == 1 else "roofline_exact"
+        line[key] = roofline_of((f1["evals"] - f0["evals"]) / 2, (f1["nnz"] - f0["nnz"]) / 2, (f1["iterations"] - f0["iterations"]) / 2,
+                                fm["align_ms"], fm["ms_step"], other, fm["phases"], n_pairs)
+        line[key]["value_alignments_per_s"] = n_pairs / (fm["ms_step"] * 1e-3)
+        fm["bt"].close()
+        line["single_pair"] = single_pair_legs(api, sm_mhz)
+    if world == 1 and a.sequence_frames >= 8:
         line["sequence_c2"] = sequence_leg(a.sequence_frames, api, dev, 0 if a.no_cpu_baseline else 6)
     print(json.dumps(line))
-    bt.close()
     if world > 1:
         dist.destroy_process_group()
 

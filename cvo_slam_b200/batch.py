@@ -129,3 +129,53 @@ class Batch:
         ms = C.c_float(0)
         self.api._check(self.lib.cvo_batch_last_align_ms(self.b, C.byref(ms)), "batch_last_align_ms")
         return ms.value
+
+
+class MultiBatch:
+    """cvo_multi_*: one list of host frames and pairs over several GPUs of this process (contiguous
+    blocks of pairs per device, one host thread per device, no exchange between devices)."""
+
+    def __init__(self, calib, params=None, n_devices=1, devices=None, max_frames=64, max_pairs=64,
+                 width=640, height=480, api=None):
+        self.api = api if api is not None else capi.load()
+        self.lib = self.api.lib
+        self.params = params if params is not None else self.api.default_params()
+        self.n_devices, self.w, self.h = n_devices, width, height
+        dv = None if devices is None else (C.c_int * n_devices)(*devices)
+        self.m = C.c_void_p()
+        self.api._check(self.lib.cvo_multi_create(C.byref(calib), C.byref(self.params), n_devices, dv,
+                                                  max_frames, max_pairs, width, height, C.byref(self.m)),
+                        "multi_create")
+
+    def close(self):
+        if self.m:
+            self.lib.cvo_multi_destroy(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align(self, bgr, depth, pairs, inner_products=True):
+        """bgr [n,h,w,3] uint8, depth [n,h,w] uint16 (host), pairs: PAIR_DTYPE array -> (results, values, nums)"""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        depth = np.ascontiguousarray(depth, dtype=np.uint16)
+        d = np.ascontiguousarray(pairs)
+        assert d.dtype == capi.PAIR_DTYPE
+        res = np.zeros(len(d), dtype=capi.RESULT_DTYPE)
+        vals = np.zeros(len(d), np.float32) if inner_products else None
+        nums = np.zeros(len(d), np.int32) if inner_products else None
+        self.api._check(self.lib.cvo_multi_align(self.m, bgr.shape[0], bgr.ctypes.data, depth.ctypes.data, len(d),
+                                                 d.ctypes.data, res.ctypes.data,
+                                                 vals.ctypes.data if inner_products else None,
+                                                 nums.ctypes.data if inner_products else None), "multi_align")
+        return res, vals, nums
+
+    def last_shares(self):
+        f = (C.c_int * self.n_devices)()
+        p = (C.c_int * self.n_devices)()
+        ms = (C.c_float * self.n_devices)()
+        self.api._check(self.lib.cvo_multi_last_shares(self.m, f, p, ms), "multi_last_shares")
+        return dict(frames=list(f), pairs=list(p), align_ms=[float(x) for x in ms])

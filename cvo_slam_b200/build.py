@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("CVO_B200_OUT") or os.path.join(HERE, "libcvo_b200.so")
 # align.cu is compiled with -fmad=false: every float/double operation of the alignment loop must
 # round exactly as the oracle's (no FMA contraction); its hot loops use explicit _rn intrinsics.
-SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": []}
+SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": [], "multi.cu": []}
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "cvo_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

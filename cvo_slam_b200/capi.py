@@ -328,6 +328,10 @@ class CudaLowLevel(LowLevel):
         lib.cvo_batch_last_align_ms.argtypes = [vp, P(C.c_float)]
         lib.cvo_batch_mark.argtypes = [vp, C.c_int]
         lib.cvo_batch_elapsed_ms.argtypes = [vp, P(C.c_float)]
+        lib.cvo_multi_create.argtypes = [P(Calib), P(Params), C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, P(vp)]
+        lib.cvo_multi_destroy.argtypes = [vp]
+        lib.cvo_multi_align.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+        lib.cvo_multi_last_shares.argtypes = [vp, vp, vp, vp]
 
     def create(self, calib, params=None, device=0):
         if params is None:

@@ -16,6 +16,16 @@ def partition(n_items, rank, world):
     return np.arange(rank, n_items, world, dtype=np.int64)
 
 
+def partition_blocks(n_items, rank, world):
+    """Contiguous blocks: rank r owns items [r * ceil(n / world), (r + 1) * ceil(n / world)).  In the
+    verification pattern consecutive pairs share their fixed keyframe, so a block touches a compact set of
+    frames and a rank selects points only for those (an interleave makes every rank select almost every
+    frame); the same split as cvo_multi_align (csrc/multi.cu).  Iteration-count variance inside a block is
+    absorbed by the per-GPU pair queue."""
+    per = (n_items + world - 1) // world
+    return np.arange(min(n_items, per * rank), min(n_items, per * (rank + 1)), dtype=np.int64)
+
+
 def frames_needed(pairs, idx):
     """Sorted unique frame ids touched by the pairs `idx` of `pairs` (array [n, 2])."""
     pairs = np.asarray(pairs).reshape(-1, 2)

@@ -240,6 +240,24 @@ int cvo_batch_last_align_ms(cvo_batch *b, float *ms);
 int cvo_batch_mark(cvo_batch *b, int which);
 int cvo_batch_elapsed_ms(cvo_batch *b, float *ms);
 
+/* ---- one list of frames and pairs over several GPUs of this process ----------------------------
+ * SURVEY section 8b lists a batch entry with an n_devices argument: the candidate loop of
+ * src/keyframe_graph.cpp:622-731 with the pairs split into n_devices contiguous blocks (section 8e: pairs
+ * shard, no collective).  Each device uploads and selects only the frames its block touches; one host
+ * thread per device; results land in the caller's array in pair order. */
+typedef struct cvo_multi cvo_multi;
+/* devices: n_devices CUDA ordinals, or NULL for 0..n_devices-1 */
+int cvo_multi_create(const cvo_calib *calib, const cvo_params *params, int n_devices, const int *devices,
+                     int max_frames, int max_pairs, int width, int height, cvo_multi **out);
+int cvo_multi_destroy(cvo_multi *m);
+/* host images of n_frames frames (tightly packed BGR8 / depth u16 planes) and n_pairs pairs indexing
+ * them -> results[n_pairs]; values / nums (both or neither may be NULL) receive the post-alignment
+ * inner product <T*moving, fixed> of every pair (cvo.cpp:545). */
+int cvo_multi_align(cvo_multi *m, int n_frames, const uint8_t *bgr, const uint16_t *depth, int n_pairs,
+                    const cvo_pair_desc *pairs, cvo_align_result *results, float *values, int *nums);
+/* per device, for the last cvo_multi_align: frames selected, pairs aligned, device time of the align kernel */
+int cvo_multi_last_shares(cvo_multi *m, int *frames, int *pairs, float *align_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -850,3 +850,64 @@ def test_selected_points_device_pointer(cuda_api, tum_calib, pair_c1):
     assert rt.cudaMemcpy(out.ctypes.data, ptr, n * 8, 2) == 0   # cudaMemcpyDeviceToHost
     assert np.array_equal(out, host)
     cuda_api.destroy(h)
+
+
+def test_multi_device_entry_matches_single_batch(cuda_api, tum_calib):
+    """cvo_multi_align (one list of host frames and pairs over n devices, contiguous blocks of pairs, one host
+    thread per device) gives the bits of one cvo_batch on one GPU.  With a single GPU in the box the two
+    "devices" are the same ordinal twice: the block split, the frame remapping and the threads are the same."""
+    import torch
+    from cvo_slam_b200 import batch as B, synth
+    scene = synth.make_scene(8)
+    rng = np.random.default_rng(8)
+    poses = [synth.pose()] + [synth.pose(rng.normal(0, 6e-3, 3), rng.normal(0, 8e-3, 3)) for _ in range(5)]
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=80 + k)) for k, P in enumerate(poses)]
+    bgr = np.stack([f[0] for f in frames])
+    dep = np.stack([f[1] for f in frames])
+    pairs = [(0, 1), (0, 2), (1, 2), (2, 3), (3, 4), (4, 5), (5, 3), (5, 0), (2, 0)]
+    bt = B.Batch(tum_calib, max_frames=6, max_pairs=len(pairs), width=640, height=480)
+    bt.set_frames(bgr, dep)
+    desc = bt.make_pairs(pairs)
+    ref = bt.align(desc)
+    rv, rn = bt.inner_product(desc, ref)
+    bt.close()
+    have = torch.cuda.device_count()
+    for devices in ([0], [0, 1 % have], [0, 1 % have, 2 % have]):
+        mb = B.MultiBatch(tum_calib, n_devices=len(devices), devices=devices, max_frames=6, max_pairs=len(pairs))
+        res, vals, nums = mb.align(bgr, dep, desc)
+        sh = mb.last_shares()
+        assert sum(sh["pairs"]) == len(pairs) and max(sh["frames"]) <= 6
+        assert np.array_equal(res["transform"], ref["transform"]) and np.array_equal(res["iterations"], ref["iterations"])
+        assert np.array_equal(res["last_iter_transform"], ref["last_iter_transform"])
+        assert np.array_equal(vals, rv) and np.array_equal(nums, rn)
+        mb.close()
+    # invalid arguments
+    mb = B.MultiBatch(tum_calib, n_devices=1, max_frames=6, max_pairs=4)
+    bad = desc[:2].copy()
+    bad["moving_frame"][0] = 17
+    assert mb.lib.cvo_multi_align(mb.m, 6, bgr.ctypes.data, dep.ctypes.data, 2, bad.ctypes.data,
+                                  np.zeros(2, dtype=ref.dtype).ctypes.data, None, None) == -1
+    mb.close()
+
+
+def test_sharded_bench_two_gpus(tmp_path):
+    """The strong-scaling arm of bench.py (one list of pairs sharded over the ranks, final gather on rank 0) on two
+    GPUs: the gathered results equal the single-GPU results to the bit (bench.py asserts it inside the run)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--frames", "64", "--steps", "1",
+           "--warmup", "1", "--no-cpu-baseline"]
+    out = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["scaling"] == "strong" and line["n_gpus"] == 2
+    assert line["shard_check"]["bit_identical"] is True
+    assert line["check"]["pairs_with_error_status"] == 0
+    assert line["weak"]["scaling"] == "weak"
