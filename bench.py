@@ -439,8 +439,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_arm(idx, noise_salt, steps, warmup, exp_mode, with_e2e=True, sample_clocks=False):
-        """Times `steps` steps over the pairs `idx` (global indices) on this rank -> dict of measurements."""
+    def run_arm(idx, noise_salt, steps, warmup, exp_mode, with_e2e=True, sample_clocks=False, collective=True):
+        """Times `steps` steps over the pairs `idx` (global indices) on this rank -> dict of measurements.
+        collective=False: an arm only this rank runs (no barrier across ranks)."""
+        def barrier():
+            if world > 1 and collective:
+                dist.barrier()
+            torch.cuda.synchronize()
+
         need = parallel.frames_needed(pairs_np, idx)
         local = {int(f): k for k, f in enumerate(need)}
         lp = [(local[int(f)], local[int(m)]) for f, m in pairs_np[idx]]
@@ -531,7 +537,7 @@ def main():
     shard_check = None
     if strong and world > 1 and rank == 0 and "gathered" in m:
         samp = np.unique(np.linspace(0, n_pairs - 1, 128).astype(np.int64))
-        chk = run_arm(samp, 0, 1, 0, a.exp_mode, with_e2e=False)
+        chk = run_arm(samp, 0, 1, 0, a.exp_mode, with_e2e=False, collective=False)
         same = bool(np.array_equal(chk["res"]["transform"], m["gathered"]["transform"][samp])
                     and np.array_equal(chk["res"]["iterations"], m["gathered"]["iterations"][samp]))
         chk["bt"].close()

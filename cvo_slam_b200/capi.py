@@ -55,7 +55,8 @@ class Params(C.Structure):
 class AlignResult(C.Structure):
     _fields_ = [("transform", C.c_float * 16), ("R", C.c_float * 9), ("T", C.c_float * 3),
                 ("ell", C.c_float), ("iterations", C.c_int32), ("iter", C.c_int32),
-                ("A_nonzero", C.c_int32), ("status", C.c_int32), ("last_iter_transform", C.c_float * 16)]
+                ("A_nonzero", C.c_int32), ("status", C.c_int32), ("num_fixed", C.c_int32), ("num_moving", C.c_int32),
+                ("last_iter_transform", C.c_float * 16)]
 
     def last_iter_transform_np(self):
         return np.array(self.last_iter_transform, dtype=np.float32).reshape(4, 4)
@@ -102,7 +103,8 @@ PAIR_DTYPE = np.dtype([("fixed_frame", "<i4"), ("moving_frame", "<i4"), ("R", "<
                        ("T", "<f4", (3,)), ("ell", "<f4")])
 RESULT_DTYPE = np.dtype([("transform", "<f4", (16,)), ("R", "<f4", (9,)), ("T", "<f4", (3,)),
                          ("ell", "<f4"), ("iterations", "<i4"), ("iter", "<i4"),
-                         ("A_nonzero", "<i4"), ("status", "<i4"), ("last_iter_transform", "<f4", (16,))])
+                         ("A_nonzero", "<i4"), ("status", "<i4"), ("num_fixed", "<i4"), ("num_moving", "<i4"),
+                         ("last_iter_transform", "<f4", (16,))])
 assert PAIR_DTYPE.itemsize == C.sizeof(PairDesc)
 assert RESULT_DTYPE.itemsize == C.sizeof(AlignResult)
 

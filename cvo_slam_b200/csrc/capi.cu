@@ -36,8 +36,9 @@ int arena_alloc(CloudArena &a, int frames, int cap) {
     CVO_CUDA_TRY(cudaMalloc(&a.f03, n * sizeof(float4)));
     CVO_CUDA_TRY(cudaMalloc(&a.f4, n * sizeof(float)));
     CVO_CUDA_TRY(cudaMalloc(&a.pix, n * sizeof(float2)));
-    CVO_CUDA_TRY(cudaMalloc(&a.n, frames * sizeof(int)));
-    CVO_CUDA_TRY(cudaMemset(a.n, 0, frames * sizeof(int)));
+    CVO_CUDA_TRY(cudaMalloc(&a.n, 2 * frames * sizeof(int)));   // counts, then overflow flags
+    CVO_CUDA_TRY(cudaMemset(a.n, 0, 2 * frames * sizeof(int)));
+    a.ovf = a.n + frames;
     return CVO_OK;
 }
 
@@ -106,6 +107,20 @@ struct cvo_batch {
 
 static const int kPinnedBytes = 1 << 16;
 
+// k_query reports "this cloud was truncated (selection overflow, or larger than the align scratch)" by
+// returning -1 - count: restore the counts, tell the caller
+static bool decode_query_counts(QueryOut *q, int n) {
+    bool trunc = false;
+    for (int i = 0; i < n; i++)
+        if (q[i].count < 0) { q[i].count = -1 - q[i].count; trunc = true; }
+    return trunc;
+}
+static int truncated_rc(const char *who) {
+    set_last_error("%s: a cloud was truncated (more selected points than the cloud arena / align scratch holds); "
+                   "the result covers the stored subset", who);
+    return CVO_ERR_CAPACITY;
+}
+
 static int handle_ensure_arena(cvo_handle *h, int need_cap) {
     if (h->arena.pos && h->arena.cap >= need_cap) return CVO_OK;
     // grow: allocate a new arena and copy the live clouds
@@ -124,6 +139,7 @@ static int handle_ensure_arena(cvo_handle *h, int need_cap) {
             CVO_CUDA_TRY(cudaMemcpy(na.pix + d_o, h->arena.pix + so, n * sizeof(float2), cudaMemcpyDeviceToDevice));
         }
         CVO_CUDA_TRY(cudaMemcpy(na.n, h->arena.n, 3 * sizeof(int), cudaMemcpyDeviceToDevice));
+        CVO_CUDA_TRY(cudaMemcpy(na.ovf, h->arena.ovf, 3 * sizeof(int), cudaMemcpyDeviceToDevice));
         arena_free(h->arena);
     }
     h->arena = na;
@@ -306,13 +322,18 @@ int cvo_set_cloud(cvo_handle *h, int slot, int n, const float *positions, const 
         f4[i] = features[5 * i + 4];
     }
     size_t o = (size_t)k * h->arena.cap;
+    // on the handle's own (non-blocking) stream, so that the uploads are ordered before the kernels the next
+    // calls launch there; the host vectors die at return, so wait for the copies
+    const int zero = 0;
     if (n > 0) {
-        CVO_CUDA_TRY(cudaMemcpy(h->arena.pos + o, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
-        CVO_CUDA_TRY(cudaMemcpy(h->arena.f03 + o, f03.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
-        CVO_CUDA_TRY(cudaMemcpy(h->arena.f4 + o, f4.data(), n * sizeof(float), cudaMemcpyHostToDevice));
-        CVO_CUDA_TRY(cudaMemcpy(h->arena.pix + o, pix.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+        CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.pos + o, pos.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.f03 + o, f03.data(), n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.f4 + o, f4.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.pix + o, pix.data(), n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     }
-    CVO_CUDA_TRY(cudaMemcpy(h->arena.n + k, &n, sizeof(int), cudaMemcpyHostToDevice));
+    CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.n + k, &n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA_TRY(cudaMemcpyAsync(h->arena.ovf + k, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CVO_OK;
 }
 
@@ -337,6 +358,9 @@ int cvo_copy_cloud(cvo_handle *dst, int dst_slot, cvo_handle *src, int src_slot)
     CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.f4 + d_o, src->arena.f4 + so, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.pix + d_o, src->arena.pix + so, n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
     CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.n + kd, src->arena.n + ks, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    CVO_CUDA_TRY(cudaMemcpyAsync(dst->arena.ovf + kd, src->arena.ovf + ks, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    // the source handle's owner may overwrite the slot (set_frame on ITS stream) as soon as this returns
+    CVO_CUDA_TRY(cudaStreamSynchronize(st));
     return CVO_OK;
 }
 
@@ -353,9 +377,11 @@ int cvo_slot_size(cvo_handle *h, int slot, int *n) {
     *n = 0;
     if (h->slot_idx[slot] < 0) return CVO_ERR_NOT_INIT;
     CVO_CUDA_TRY(cudaSetDevice(h->device));
+    int ovf = 0;
     CVO_CUDA_TRY(cudaMemcpyAsync(n, h->arena.n + h->slot_idx[slot], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA_TRY(cudaMemcpyAsync(&ovf, h->arena.ovf + h->slot_idx[slot], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return CVO_OK;
+    return ovf ? truncated_rc("cvo_slot_size") : CVO_OK;   // *n = the points kept
 }
 
 int cvo_set_RT(cvo_handle *h, const float R[9], const float T[3]) {
@@ -449,28 +475,29 @@ static int handle_query(cvo_handle *h, int slot_a, const float *Ta, int slot_b, 
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(ho, h->d_qo, sizeof(QueryOut), cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const bool trunc = decode_query_counts(ho, 1);
     *res = *ho;
-    return CVO_OK;
+    return trunc ? CVO_ERR_CAPACITY : CVO_OK;
 }
 
 int cvo_inner_product(cvo_handle *h, int slot_a, const float *Ta, int slot_b, float *value, int *num) {
     if (!value || !num) return CVO_ERR_INVALID;
     QueryOut q;
     int rc = handle_query(h, slot_a, Ta, slot_b, 0, &q);
-    if (rc != CVO_OK) return rc;
+    if (rc != CVO_OK && rc != CVO_ERR_CAPACITY) return rc;
     *value = (float)q.sum;                 // inn_p(float v, int n, int n_e)   cvo.hpp:71
     *num = q.count == 0 ? 1 : q.count;     // `if (sum == 0) sum = 1;`          cvo.cpp:455
-    return CVO_OK;
+    return rc == CVO_ERR_CAPACITY ? truncated_rc("cvo_inner_product") : CVO_OK;
 }
 
 int cvo_hessian(cvo_handle *h, int slot_a, const float *Ta, int slot_b, double H[36], int *inliers) {
     if (!H || !inliers) return CVO_ERR_INVALID;
     QueryOut q;
     int rc = handle_query(h, slot_a, Ta, slot_b, 1, &q);
-    if (rc != CVO_OK) return rc;
+    if (rc != CVO_OK && rc != CVO_ERR_CAPACITY) return rc;
     *inliers = q.count;
     finish_hessian_host(q, H);
-    return CVO_OK;
+    return rc == CVO_ERR_CAPACITY ? truncated_rc("cvo_hessian") : CVO_OK;
 }
 
 // cvo::compute_innerproduct (cvo.cpp:475-503) in one launch: the four inner products and the
@@ -501,13 +528,14 @@ int cvo_compute_innerproduct(cvo_handle *h, const float tran[16], float values[4
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(ho, h->d_qo, sizeof(QueryOut) * 5, cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const bool trunc = decode_query_counts(ho, 5);
     for (int k = 0; k < 4; k++) {
         values[k] = (float)ho[k].sum;
         nums[k] = ho[k].count == 0 ? 1 : ho[k].count;
     }
     *inliers = ho[4].count;
     finish_hessian_host(ho[4], H);
-    return CVO_OK;
+    return trunc ? truncated_rc("cvo_compute_innerproduct") : CVO_OK;
 }
 
 // the accept rule of the reference's only caller (src/keyframe_graph.cpp:711-712)
@@ -547,6 +575,7 @@ int cvo_compute_innerproduct_lc(cvo_handle *h, const float prior_tran[16], const
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(ho, h->d_qo, sizeof(QueryOut) * 8, cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const bool trunc = decode_query_counts(ho, 8);
     for (int k = 0; k < 6; k++) {
         out->value[k] = (float)ho[k].sum;
         out->num[k] = ho[k].count == 0 ? 1 : ho[k].count;
@@ -555,7 +584,7 @@ int cvo_compute_innerproduct_lc(cvo_handle *h, const float prior_tran[16], const
     finish_hessian_host(ho[6], out->post_hessian);
     out->inliers_pnpransac = ho[7].count;
     finish_lc_record(out);
-    return CVO_OK;
+    return trunc ? truncated_rc("cvo_compute_innerproduct_lc") : CVO_OK;
 }
 
 int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n) {
@@ -748,9 +777,11 @@ int cvo_batch_set_frames_device(cvo_batch *b, int first, int n, const uint8_t *b
 int cvo_batch_frame_size(cvo_batch *b, int frame, int *n) {
     if (!b || !n || frame < 0 || frame >= b->max_frames) return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
+    int ovf = 0;
     CVO_CUDA_TRY(cudaMemcpyAsync(n, b->arena.n + frame, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CVO_CUDA_TRY(cudaMemcpyAsync(&ovf, b->arena.ovf + frame, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
-    return CVO_OK;
+    return ovf ? truncated_rc("cvo_batch_frame_size") : CVO_OK;
 }
 
 int cvo_batch_align(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, cvo_align_result *results) {
@@ -787,6 +818,9 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
     if (n_pairs == 0) return CVO_OK;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
     for (int i = 0; i < n_pairs; i++) {
+        if (pairs[i].fixed_frame < 0 || pairs[i].fixed_frame >= b->max_frames || pairs[i].moving_frame < 0 ||
+            pairs[i].moving_frame >= b->max_frames)
+            return CVO_ERR_INVALID;
         QueryTask &q = b->h_q[i];
         q.a = b->arena.view(pairs[i].moving_frame);
         q.b = b->arena.view(pairs[i].fixed_frame);
@@ -799,11 +833,12 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_qo, b->d_qo, sizeof(QueryOut) * n_pairs, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    const bool trunc = decode_query_counts(b->h_qo, n_pairs);
     for (int i = 0; i < n_pairs; i++) {
         values[i] = (float)b->h_qo[i].sum;
         nums[i] = b->h_qo[i].count == 0 ? 1 : b->h_qo[i].count;
     }
-    return CVO_OK;
+    return trunc ? truncated_rc("cvo_batch_inner_product") : CVO_OK;
 }
 
 // compute_innerproduct_lc for every pair of a batch.  One k_verify_lc CTA per pair evaluates the
@@ -883,6 +918,8 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, c
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lco, b->d_lco, sizeof(LcOut) * n_pairs, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lcqo, b->d_lcqo, sizeof(QueryOut) * nq, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
+    bool lc_trunc = decode_query_counts(b->h_lcqo, nq);
+    for (int i = 0; i < n_pairs; i++) lc_trunc = lc_trunc || b->h_lco[i].truncated != 0;
     for (int i = 0; i < n_pairs; i++) {
         const LcOut &o = b->h_lco[i];
         cvo_lc_result &r = out[i];
@@ -900,7 +937,7 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, c
         r.inliers_pnpransac = o.inliers[1];
         finish_lc_record(&r);
     }
-    return CVO_OK;
+    return lc_trunc ? truncated_rc("cvo_batch_verify_lc") : CVO_OK;
 }
 
 int cvo_batch_stats(cvo_batch *b, int64_t stats[4]) {

@@ -32,6 +32,7 @@ struct CloudView {
     const float *f4;
     const float2 *pix;   // selected pixel (x, y)  (frame::selected_points)
     const int *n;        // device-resident point count
+    const int *ovf;      // != 0: the selection found more points than the arena holds (the cloud is truncated)
 };
 
 // F clouds of equal capacity in one allocation (frame k at offset k*cap in every array).
@@ -43,11 +44,12 @@ struct CloudArena {
     float *f4 = nullptr;
     float2 *pix = nullptr;
     int *n = nullptr;       // [frames]
+    int *ovf = nullptr;     // [frames] selection overflow flags
     int cap = 0;
     int frames = 0;
     CloudView view(int k) const {
         size_t o = (size_t)k * cap;
-        return CloudView{pos + o, f03 + o, f4 + o, pix + o, n + k};
+        return CloudView{pos + o, f03 + o, f4 + o, pix + o, n + k, ovf + k};
     }
 };
 
@@ -132,6 +134,7 @@ struct LcTask {
     float ell;
 };
 struct LcOut {
+    int truncated;          // a cloud of the pair was truncated (selection overflow / larger than the scratch)
     double sum[4];
     double H[36];           // post_hessian, scaled and eigenvalue-shifted (cvo.cpp:726-758)
     int count[4];

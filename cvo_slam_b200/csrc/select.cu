@@ -387,6 +387,7 @@ struct ArenaDev {
     float *f4;
     float2 *pix;
     int *n;
+    int *ovf;
     int cap;
     int first;
 };
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
         st->n_out = total_out;
         st->overflow = total_out > A.cap;
         A.n[A.first + f] = min(total_out, A.cap);
+        A.ovf[A.first + f] = total_out > A.cap ? 1 : 0;   // surfaces as CVO_ERR_CAPACITY / CVO_ERR_PAIR_OVERFLOW downstream
     }
 }
 
@@ -624,7 +626,7 @@ int sel_run(SelWorkspace *ws, int n, const uint8_t *bgr_dev, const uint16_t *dep
         tiles = ((d.w + 3) / 4) * ((d.h + 3) / 4);
         k_select<<<dim3((tiles * 16 + 255) / 256, fn), 256, 0, stream>>>(d, 1);
     }
-    ArenaDev A{arena.pos, arena.f03, arena.f4, arena.pix, arena.n, arena.cap, first};
+    ArenaDev A{arena.pos, arena.f03, arena.f4, arena.pix, arena.n, arena.ovf, arena.cap, first};
     k_compact<<<fn, 1024, 0, stream>>>(d, A, bgr_dev, bgr_stride, depth_dev, depth_stride);
     if (launches) *launches += 9;
     CVO_CUDA_TRY(cudaGetLastError());

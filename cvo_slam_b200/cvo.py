@@ -82,6 +82,7 @@ class Cvo:
         self.pre_pc_init = False
         self.num_fixed = 0
         self.num_moving = 0
+        self._sizes_valid = False
         self.A_nonzero = 0
         self.last_result = None
 
@@ -103,6 +104,7 @@ class Cvo:
             self.init = True
             return
         self.api.set_frame(self.h, SLOT_MOVING, rgb_img, dep_img)
+        self._sizes_valid = False     # the reference refreshes num_fixed / num_moving here (cvo.cpp:370-371)
         self.A_nonzero = 0
 
     # ---- cvo.cpp:763-821 -------------------------------------------------------------------
@@ -112,6 +114,7 @@ class Cvo:
         if res.iter >= 0:
             self.iter = res.iter          # `iter` is only written on break (cvo.cpp:783,805)
         self.A_nonzero = res.A_nonzero
+        self.num_fixed, self.num_moving, self._sizes_valid = int(res.num_fixed), int(res.num_moving), True
         # cvo.cpp:815-816: `transform` as the last executed iteration's update_tf() left it
         last = res.last_iter_transform_np()
         self.prev_transform = last.copy()
@@ -214,7 +217,13 @@ class Cvo:
 
     # ---- getters (cvo.hpp:268-276) -------------------------------------------------------------
     def get_fixed_and_moving_number(self):
-        return self.api.slot_size(self.h, SLOT_FIXED), self.api.slot_size(self.h, SLOT_MOVING)
+        """What set_pcd cached (cvo.cpp:370-371) — also after update_fixed_pcd has moved the clouds, like the
+        reference; align() refreshes the cache from its result, so no device sync on the tracking path."""
+        if not self._sizes_valid and self.init:
+            nf, nm = self.api.slot_size(self.h, SLOT_FIXED), self.api.slot_size(self.h, SLOT_MOVING)
+            if nf >= 0 and nm >= 0:
+                self.num_fixed, self.num_moving, self._sizes_valid = nf, nm, True
+        return self.num_fixed, self.num_moving
 
     def get_iteration_number(self):
         return self.iter

@@ -49,6 +49,20 @@ struct Mat44f {
     float &operator()(int r, int c) { return m[r * 4 + c]; }
     float operator()(int r, int c) const { return m[r * 4 + c]; }
 };
+struct Mat33f {
+    float m[9];
+    float &operator()(int r, int c) { return m[r * 3 + c]; }
+    float operator()(int r, int c) const { return m[r * 3 + c]; }
+};
+struct Vec3f {
+    float v[3];
+    float &operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+    float &operator[](int i) { return v[i]; }
+    float operator[](int i) const { return v[i]; }
+};
+/* The part of Eigen::Affine3f the callers of cvo::cvo use (src/local_tracker.cpp, src/keyframe_graph.cpp):
+ * Identity(), matrix(), linear(), translation(), inverse(), operator*, cast<>(). */
 struct Affine3f {
     Mat44f mat;
     Affine3f() { *this = Identity(); }
@@ -59,6 +73,23 @@ struct Affine3f {
     }
     Mat44f &matrix() { return mat; }
     const Mat44f &matrix() const { return mat; }
+    Mat33f linear() const {
+        Mat33f l;
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) l(r, c) = mat(r, c);
+        return l;
+    }
+    Mat33f rotation() const { return linear(); } /* (Eigen's rotation() re-orthogonalises: see reset_initial) */
+    Vec3f translation() const { Vec3f t; for (int r = 0; r < 3; r++) t[r] = mat(r, 3); return t; }
+    Affine3f operator*(const Affine3f &o) const {
+        Affine3f out(0);
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) {
+            float s = 0;
+            for (int k = 0; k < 4; k++) s += mat(r, k) * o.mat(k, c);
+            out.mat(r, c) = s;
+        }
+        return out;
+    }
+    Affine3f inverse() const; /* cofactor inverse of the linear part (defined below, detail::inv_affine) */
     template <class T> Affine3f cast() const { return *this; }
 private:
     explicit Affine3f(int) {}
@@ -157,6 +188,15 @@ inline void inv_affine(const float a[16], float o[16]) {
     o[12] = o[13] = o[14] = 0.f;
     o[15] = 1.f;
 }
+}  // namespace detail
+#ifndef CVO_B200_HAVE_EIGEN_OPENCV
+inline shim::Affine3f shim::Affine3f::inverse() const {
+    shim::Affine3f out = Identity();
+    detail::inv_affine(mat.m, out.mat.m);
+    return out;
+}
+#endif
+namespace detail {
 /* "Key: value" lines of an OpenCV FileStorage YAML (cvo.cpp:58-64 reads five scalars) */
 inline bool yaml_scalar(const std::string &path, const std::string &key, float &out) {
     std::ifstream f(path.c_str());
@@ -176,10 +216,24 @@ inline bool yaml_scalar(const std::string &path, const std::string &key, float &
 class cvo {
 private:
     cvo_handle *h_;
+    cvo_handle *scratch_;  /* second handle, same parameters and device, for the public host-cloud entry points */
+    cvo_params prm_;       /* the constructor's parameters (defaults of cvo.cpp:35-51 unless given)            */
+    int device_;
     bool pre_pc_init;
+    bool sizes_valid_;     /* num_fixed / num_moving are current (cvo.cpp:370-371 sets them in set_pcd)        */
     int num_fixed, num_moving;
     int A_nonzero;
     cvo_calib cam_info;
+
+    cvo_handle *scratch_handle() {
+        if (!scratch_ && cvo_create(&cam_info, &prm_, device_, &scratch_) != CVO_OK) scratch_ = nullptr;
+        if (scratch_) {
+            float ell = prm_.ell_init;
+            cvo_get_ell(h_, &ell); /* the queries run at the member ell, whatever align left (cvo.cpp:391) */
+            cvo_set_ell(scratch_, ell);
+        }
+        return scratch_;
+    }
 
     void check(int rc, const char *what) const {
         if (rc != CVO_OK && rc != CVO_ERR_NOT_INIT)
@@ -213,6 +267,9 @@ private:
     }
 
 public:
+#ifdef CVO_B200_HAVE_EIGEN_OPENCV
+    EIGEN_MAKE_ALIGNED_OPERATOR_NEW /* reference cvo.hpp:146: `new cvo::cvo` (local_tracker.cpp:48-49) with Affine3f members */
+#endif
     /* public variables (cvo.hpp:137-146) */
     bool first_frame;
     bool init;
@@ -223,8 +280,10 @@ public:
 
     /* cvo.cpp:18-71.  `device` is new (default 0); everything else as in the reference. */
     explicit cvo(const std::string &calib_file, int device = 0, const cvo_params *params = nullptr)
-        : h_(nullptr), pre_pc_init(false), num_fixed(0), num_moving(0), A_nonzero(0), first_frame(true),
-          init(false), iter(0) {
+        : h_(nullptr), scratch_(nullptr), device_(device), pre_pc_init(false), sizes_valid_(false), num_fixed(0),
+          num_moving(0), A_nonzero(0), first_frame(true), init(false), iter(0) {
+        if (params) prm_ = *params;
+        else cvo_default_params(&prm_);
         cam_info.fx = cam_info.fy = cam_info.cx = cam_info.cy = 0.f;
         cam_info.scaling_factor = 0.f;
         detail::yaml_scalar(calib_file, "Camera.fx", cam_info.fx);
@@ -235,10 +294,10 @@ public:
         transform = affine3f_t::Identity();
         prev_transform = affine3f_t::Identity();
         accum_transform = affine3f_t::Identity();
-        int rc = cvo_create(&cam_info, params, device, &h_);
+        int rc = cvo_create(&cam_info, &prm_, device_, &h_);
         if (rc != CVO_OK) throw std::runtime_error(std::string("cvo_create: ") + cvo_last_error());
     }
-    ~cvo() { cvo_destroy(h_); }
+    ~cvo() { cvo_destroy(scratch_); cvo_destroy(h_); }
     cvo(const cvo &) = delete;
     cvo &operator=(const cvo &) = delete;
 
@@ -249,6 +308,7 @@ public:
                             (const uint16_t *)dep_img.data, (size_t)dep_img.step, RGB_img.cols, RGB_img.rows),
               "cvo_set_frame");
         if (!init) { init = true; return; }
+        sizes_valid_ = false; /* the reference refreshes num_fixed / num_moving here (cvo.cpp:370-371) */
         A_nonzero = 0;
     }
 
@@ -260,6 +320,9 @@ public:
         if (rc != CVO_OK && rc != CVO_ERR_PAIR_OVERFLOW) return;
         if (r.iter >= 0) iter = r.iter; /* `iter` is written only on break (cvo.cpp:783,805) */
         A_nonzero = r.A_nonzero;
+        num_fixed = r.num_fixed;   /* the sizes set_pcd would have cached, without a device sync */
+        num_moving = r.num_moving;
+        sizes_valid_ = true;
         /* cvo.cpp:815-816: prev_transform / accum_transform take `transform` as the LAST executed
          * iteration's update_tf() left it, not the final one */
         detail::from_rows(r.last_iter_transform, prev_transform);
@@ -288,38 +351,26 @@ public:
     /* cvo.cpp:388-459 and :620-759 on caller-supplied host clouds (upload path) */
     const inn_p function_inner_product(point_cloud_t *cloud_a, point_cloud_t *cloud_b) {
         cvo_handle *keep = h_;
-        cvo_handle *tmp = nullptr;
-        cvo_params prm;
-        cvo_default_params(&prm);
-        if (cvo_create(&cam_info, &prm, 0, &tmp) != CVO_OK) return inn_p(0.f, 1, 0);
-        float ell = prm.ell_init;
-        cvo_get_ell(keep, &ell);
-        cvo_set_ell(tmp, ell);
+        cvo_handle *tmp = scratch_handle(); /* same sigma / sp_thres / c_ell / c_sigma and device as this object */
+        if (!tmp) return inn_p(0.f, 1, 0);
         h_ = tmp;
         upload(CVO_SLOT_MOVING, cloud_a);
         upload(CVO_SLOT_FIXED, cloud_b);
         inn_p r = inner(CVO_SLOT_MOVING, nullptr, CVO_SLOT_FIXED);
         h_ = keep;
-        cvo_destroy(tmp);
         return r;
     }
     matrix66d_t se3_Hessian(point_cloud_t *cloud_a, point_cloud_t *cloud_b, int &inliers) {
         cvo_handle *keep = h_;
-        cvo_handle *tmp = nullptr;
-        cvo_params prm;
-        cvo_default_params(&prm);
         matrix66d_t I;
         for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) I(r, c) = (r == c);
-        if (cvo_create(&cam_info, &prm, 0, &tmp) != CVO_OK) return I;
-        float ell = prm.ell_init;
-        cvo_get_ell(keep, &ell);
-        cvo_set_ell(tmp, ell);
+        cvo_handle *tmp = scratch_handle();
+        if (!tmp) return I;
         h_ = tmp;
         upload(CVO_SLOT_MOVING, cloud_a);
         upload(CVO_SLOT_FIXED, cloud_b);
         matrix66d_t H = hess(CVO_SLOT_MOVING, nullptr, CVO_SLOT_FIXED, inliers);
         h_ = keep;
-        cvo_destroy(tmp);
         return H;
     }
 
@@ -381,6 +432,20 @@ public:
     }
     void reset_transform(affine3f_t &odometry) { transform = odometry; }
     affine3f_t reset_initial(affine3f_t &odometry) {
+#ifdef CVO_B200_HAVE_EIGEN_OPENCV
+        /* with the real Eigen this IS the reference's code (cvo.cpp:611-618), including rotation(), which
+         * re-orthogonalises the linear part through an SVD */
+        Eigen::Affine3f init_e = (transform * odometry).inverse();
+        const Eigen::Matrix3f Re = init_e.rotation();
+        const Eigen::Vector3f Te = init_e.translation();
+        float Rr[9], Tr[3];
+        for (int r = 0; r < 3; r++) { for (int k = 0; k < 3; k++) Rr[r * 3 + k] = Re(r, k); Tr[r] = Te(r); }
+        cvo_set_RT(h_, Rr, Tr);
+        return init_e.inverse();
+#else
+        /* stand-in types: the same product and cofactor inverse in float; R is the linear part itself where
+         * Eigen's rotation() would re-orthogonalise it (a ~1e-7 difference in the prior; the oracle and the
+         * Python mirror make the same choice, so the parity tests compare like with like) */
         float a[16], b[16], c[16], init_m[16], back[16];
         detail::to_rows(transform, a);
         detail::to_rows(odometry, b);
@@ -393,12 +458,22 @@ public:
         affine3f_t out = affine3f_t::Identity();
         detail::from_rows(back, out);
         return out;
+#endif
     }
 
     /* getters (cvo.hpp:268-276) */
     void get_fixed_and_moving_number(int &fixed_num, int &moving_num) {
-        cvo_slot_size(h_, CVO_SLOT_FIXED, &num_fixed);
-        cvo_slot_size(h_, CVO_SLOT_MOVING, &num_moving);
+        /* the reference returns what set_pcd cached (cvo.cpp:370-371), also after update_fixed_pcd has moved
+         * the clouds; align() refreshes the cache from its result, so this costs a device sync only when it is
+         * called between set_pcd and align */
+        if (!sizes_valid_ && init) {
+            int nf = 0, nm = 0;
+            if (cvo_slot_size(h_, CVO_SLOT_FIXED, &nf) != CVO_ERR_NOT_INIT && cvo_slot_size(h_, CVO_SLOT_MOVING, &nm) != CVO_ERR_NOT_INIT) {
+                num_fixed = nf;
+                num_moving = nm;
+                sizes_valid_ = true;
+            }
+        }
         fixed_num = num_fixed;
         moving_num = num_moving;
     }

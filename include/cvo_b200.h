@@ -76,6 +76,8 @@ typedef struct cvo_align_result {
     int32_t iter;        /* the reference's `iter` member: k at break; -1 if no break      */
     int32_t A_nonzero;   /* nnz of A at the last compute_flow (cvo.cpp:197-229)            */
     int32_t status;      /* CVO_OK or CVO_ERR_PAIR_OVERFLOW                                 */
+    int32_t num_fixed;   /* points of the fixed / moving cloud this alignment ran on: what set_pcd  */
+    int32_t num_moving;  /* caches in num_fixed / num_moving (cvo.cpp:370-371), without a sync     */
     float last_iter_transform[16]; /* `transform` as update_tf() left it at the top of the LAST executed
                           * iteration: what cvo.cpp:815-816 store in prev_transform and multiply into
                           * accum_transform before the final update_tf()                   */

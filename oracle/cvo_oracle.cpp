@@ -1003,6 +1003,8 @@ struct OracleCvo {
         if (out) {
             memset(out, 0, sizeof(*out));
             memcpy(out->last_iter_transform, last_tf, sizeof(last_tf));
+            out->num_fixed = slot[CVO_SLOT_FIXED].n;
+            out->num_moving = slot[CVO_SLOT_MOVING].n;
             for (int i = 0; i < 3; i++) {
                 for (int j = 0; j < 3; j++) { out->transform[i * 4 + j] = tf_lin.m[i][j]; out->R[i * 3 + j] = R.m[i][j]; }
                 out->transform[i * 4 + 3] = tf_tr[i];

@@ -19,6 +19,7 @@ from cvo_slam_b200.capi import (Calib, LowLevel, Params, CVO_OK)  # noqa: E402  
 
 LIB = os.path.join(HERE, "libcvo_oracle.so")
 LIB_KD = os.path.join(HERE, "_ref", "libcvo_oracle_kd.so")
+LIB_REFSEL = os.path.join(HERE, "_ref", "libref_select.so")   # the reference's own selector sources, compiled here
 
 SEARCH_GRID, SEARCH_BRUTE, SEARCH_NANOFLANN = 0, 1, 2
 
@@ -31,6 +32,8 @@ def build(force=False):
     if os.path.exists("/root/reference/thirdparty/cvo/thirdparty/nanoflann.hpp"):
         if force or not os.path.exists(LIB_KD) or os.path.getmtime(LIB_KD) < os.path.getmtime(src):
             subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    if os.path.exists("/root/reference/thirdparty/cvo/src/pcd_generator.cpp"):
+        subprocess.check_call(["make", "-C", HERE, "refsel"], stdout=subprocess.DEVNULL)
 
 
 class OracleLowLevel(LowLevel):
@@ -174,3 +177,42 @@ def load(kd=None):
             raise ImportError(f"{path} not built")
         _cache[path] = OracleLowLevel(C.CDLL(path))
     return _cache[path]
+
+
+class RefSelect:
+    """The reference's own pcd_generator::create_pointcloud (pcd_generator.cpp + PixelSelector2.cpp compiled
+    where they lie, oracle/ref_select.cpp): status map, selected pixels, positions, features of one frame."""
+
+    def __init__(self, lib):
+        self.lib = lib
+        vp = C.c_void_p
+        lib.refsel_run.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp]
+        lib.refsel_run.restype = C.c_int
+
+    def run(self, bgr, depth, calib, num_want=3000, feature_type=1, gray_mode=0):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        h, w = depth.shape
+        cal = np.array([calib.scaling_factor, calib.fx, calib.fy, calib.cx, calib.cy], np.float32)
+        cap = w * h
+        smap = np.zeros((h, w), np.float32)
+        gray = np.zeros((h, w), np.float32)
+        pix = np.zeros((cap, 2), np.float32)
+        pos = np.zeros((cap, 3), np.float32)
+        feat = np.zeros((cap, 5), np.float32)
+        n = self.lib.refsel_run(bgr.ctypes.data, depth.ctypes.data, w, h, cal.ctypes.data, int(num_want), int(feature_type),
+                                int(gray_mode), smap.ctypes.data, pix.ctypes.data, pos.ctypes.data, feat.ctypes.data, cap,
+                                gray.ctypes.data)
+        assert n >= 0
+        return dict(map=smap.astype(np.uint8), gray=gray.astype(np.uint8), pix=pix[:n].copy(), pos=pos[:n].copy(),
+                    feat=feat[:n].copy(), n=n)
+
+
+def load_refsel():
+    """-> RefSelect, or None where the reference (and hence oracle/_ref/libref_select.so) is not available."""
+    build()
+    if not os.path.exists(LIB_REFSEL):
+        return None
+    if LIB_REFSEL not in _cache:
+        _cache[LIB_REFSEL] = RefSelect(C.CDLL(LIB_REFSEL))
+    return _cache[LIB_REFSEL]

@@ -551,7 +551,9 @@ def test_cpp_dropin_matches_python_path(cuda_api, tum_calib, pair_c1, tmp_path):
     fip = [l.split() for l in out.splitlines() if l.startswith("fip ")][0]
     assert float(fip[1]) == pytest.approx(float(fip[4]), rel=1e-6) and fip[2] == fip[5]   # wrapper == slot path
     assert int(fip[7]) == int(fip[2])                                                  # same pair set
-    assert "after update_fixed_pcd N %d 0" % c.get_fixed_and_moving_number()[1] in out
+    # the reference's getter returns what set_pcd cached, also after the clouds have moved (cvo.cpp:370-371, 578-582)
+    c.update_fixed_pcd()
+    assert "after update_fixed_pcd N %d %d" % c.get_fixed_and_moving_number() in out
     c.close()
 
 

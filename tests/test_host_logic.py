@@ -97,22 +97,25 @@ def test_cvo_mirror_state_shuffles(oracle_plain, tum_calib):
     api.set_cloud(h, 0, *cloud(40, 0))
     api.set_cloud(h, 1, *cloud(41, 0))
     c.init = True
+    live = lambda: (api.slot_size(h, 0), api.slot_size(h, 1))   # noqa: E731  (the device clouds themselves)
     assert c.get_fixed_and_moving_number() == (40, 41)
     c.update_fixed_pcd()                          # fixed <- moving, moving empty
-    assert c.get_fixed_and_moving_number() == (41, -1)
+    assert live() == (41, -1)
+    # the getter returns what set_pcd cached, also after the move — like the reference (cvo.cpp:370-371, 578-582)
+    assert c.get_fixed_and_moving_number() == (40, 41)
     api.set_cloud(h, 1, *cloud(42, 0))
     # reset_keyframe before any update_previous_pcd: fixed <- moving (cvo.cpp:593-596)
     odo = np.eye(4, dtype=np.float32)
     odo[:3, 3] = [0.1, 0.0, 0.0]
     c.reset_keyframe(odo)
-    assert c.get_fixed_and_moving_number() == (42, -1)
+    assert live() == (42, -1)
     assert np.array_equal(c.transform, odo)
     api.set_cloud(h, 1, *cloud(43, 0))
     c.update_previous_pcd()                       # previous <- moving
     assert api.slot_size(h, 2) == 43 and c.pre_pc_init
     api.set_cloud(h, 1, *cloud(44, 0))
     c.reset_keyframe(odo)                         # fixed <- previous, previous <- moving
-    assert c.get_fixed_and_moving_number() == (43, -1) and api.slot_size(h, 2) == 44
+    assert live() == (43, -1) and api.slot_size(h, 2) == 44
     # reset_initial: R,T = inv(transform * odom); returns its inverse (cvo.cpp:611-618)
     c.transform = odo.copy()
     back = c.reset_initial(odo)
