@@ -20,6 +20,7 @@ from cvo_slam_b200.capi import (Calib, LowLevel, Params, CVO_OK)  # noqa: E402  
 LIB = os.path.join(HERE, "libcvo_oracle.so")
 LIB_KD = os.path.join(HERE, "_ref", "libcvo_oracle_kd.so")
 LIB_REFSEL = os.path.join(HERE, "_ref", "libref_select.so")   # the reference's own selector sources, compiled here
+LIB_REFCVO = os.path.join(HERE, "_ref", "libref_cvo.so")      # the reference's own cvo.cpp / LieGroup.cpp, compiled here
 
 SEARCH_GRID, SEARCH_BRUTE, SEARCH_NANOFLANN = 0, 1, 2
 
@@ -33,7 +34,7 @@ def build(force=False):
         if force or not os.path.exists(LIB_KD) or os.path.getmtime(LIB_KD) < os.path.getmtime(src):
             subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/thirdparty/cvo/src/pcd_generator.cpp"):
-        subprocess.check_call(["make", "-C", HERE, "refsel"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", HERE, "refsel", "refcvo"], stdout=subprocess.DEVNULL)
 
 
 class OracleLowLevel(LowLevel):
@@ -216,3 +217,107 @@ def load_refsel():
     if LIB_REFSEL not in _cache:
         _cache[LIB_REFSEL] = RefSelect(C.CDLL(LIB_REFSEL))
     return _cache[LIB_REFSEL]
+
+
+class _RefRecord(C.Structure):
+    _fields_ = [("ell", C.c_float), ("omega", C.c_float * 3), ("v", C.c_float * 3), ("step", C.c_float), ("nnz", C.c_int32)]
+
+
+class RefCvo:
+    """The reference's own cvo::cvo (cvo.cpp, LieGroup.cpp, pcd_generator.cpp, PixelSelector2.cpp and its vendored
+    nanoflann compiled where they lie, oracle/ref_cvo.cpp).  One instance = one cvo object."""
+
+    def __init__(self, lib, calib):
+        self.lib = lib
+        vp = C.c_void_p
+        lib.refcvo_create.restype = vp
+        lib.refcvo_create.argtypes = [vp]
+        lib.refcvo_destroy.argtypes = [vp]
+        lib.refcvo_set_pcd.argtypes = [vp, vp, vp, C.c_int, C.c_int]
+        lib.refcvo_set_clouds.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp]
+        lib.refcvo_sizes.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.refcvo_set_state.argtypes = [vp, vp, vp, C.c_float]
+        lib.refcvo_get_state.argtypes = [vp, vp, vp, C.POINTER(C.c_float), vp]
+        lib.refcvo_iteration_at.argtypes = [vp, vp, vp, C.c_float, C.POINTER(_RefRecord), C.c_int, vp, vp]
+        lib.refcvo_align.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        lib.refcvo_compute_innerproduct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        lib.refcvo_update_fixed_pcd.argtypes = [vp]
+        lib.refcvo_reset_initial.argtypes = [vp, vp, vp]
+        lib.refcvo_set_max_iter.argtypes = [vp, C.c_int]
+        cal = np.array([calib.scaling_factor, calib.fx, calib.fy, calib.cx, calib.cy], np.float32)
+        self.h = lib.refcvo_create(cal.ctypes.data)
+        assert self.h
+
+    def close(self):
+        if self.h:
+            self.lib.refcvo_destroy(self.h)
+            self.h = None
+
+    def set_pcd(self, bgr, depth):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        self.lib.refcvo_set_pcd(self.h, bgr.ctypes.data, depth.ctypes.data, depth.shape[1], depth.shape[0])
+
+    def set_clouds(self, pos_f, feat_f, pos_m, feat_m):
+        a = [np.ascontiguousarray(x, np.float32) for x in (pos_f, feat_f, pos_m, feat_m)]
+        self.lib.refcvo_set_clouds(self.h, len(a[0]), a[0].ctypes.data, a[1].ctypes.data, len(a[2]), a[2].ctypes.data, a[3].ctypes.data)
+
+    def sizes(self):
+        nf, nm = C.c_int(0), C.c_int(0)
+        self.lib.refcvo_sizes(self.h, C.byref(nf), C.byref(nm))
+        return nf.value, nm.value
+
+    def set_state(self, R, T, ell):
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        T = np.ascontiguousarray(T, np.float32)
+        self.lib.refcvo_set_state(self.h, R.ctypes.data, T.ctypes.data, float(ell))
+
+    def get_state(self):
+        R, T, tf, ell = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(16, np.float32), C.c_float(0)
+        self.lib.refcvo_get_state(self.h, R.ctypes.data, T.ctypes.data, C.byref(ell), tf.ctypes.data)
+        return R.reshape(3, 3), T, ell.value, tf.reshape(4, 4)
+
+    def iteration_at(self, R, T, ell, cap=1 << 21):
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        T = np.ascontiguousarray(T, np.float32)
+        rec = _RefRecord()
+        ij = np.zeros((cap, 2), np.int32)
+        a = np.zeros(cap, np.float32)
+        n = self.lib.refcvo_iteration_at(self.h, R.ctypes.data, T.ctypes.data, float(ell), C.byref(rec), cap, ij.ctypes.data, a.ctypes.data)
+        return dict(ell=rec.ell, omega=np.array(rec.omega, np.float32), v=np.array(rec.v, np.float32), step=rec.step, nnz=rec.nnz,
+                    ij=ij[:n].copy(), a=a[:n].copy())
+
+    def align(self):
+        tf, last = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        it, nnz, ell = C.c_int(0), C.c_int(0), C.c_float(0)
+        self.lib.refcvo_align(self.h, tf.ctypes.data, last.ctypes.data, C.byref(it), C.byref(nnz), C.byref(ell))
+        return dict(transform=tf.reshape(4, 4), last_iter_transform=last.reshape(4, 4), iter=it.value, A_nonzero=nnz.value, ell=ell.value)
+
+    def compute_innerproduct(self, tran):
+        t = np.ascontiguousarray(tran, np.float32).reshape(16)
+        v, n, H = np.zeros(4, np.float32), np.zeros(4, np.int32), np.zeros(36, np.float64)
+        inl, cos = C.c_int(0), C.c_float(0)
+        self.lib.refcvo_compute_innerproduct(self.h, t.ctypes.data, v.ctypes.data, n.ctypes.data, H.ctypes.data, C.byref(inl), C.byref(cos))
+        return dict(values=v, nums=n, H=H.reshape(6, 6), inliers=inl.value, cos_angle=cos.value)
+
+    def update_fixed_pcd(self):
+        self.lib.refcvo_update_fixed_pcd(self.h)
+
+    def reset_initial(self, odom):
+        o = np.ascontiguousarray(odom, np.float32).reshape(16)
+        back = np.zeros(16, np.float32)
+        self.lib.refcvo_reset_initial(self.h, o.ctypes.data, back.ctypes.data)
+        return back.reshape(4, 4)
+
+    def set_max_iter(self, n):
+        self.lib.refcvo_set_max_iter(self.h, int(n))
+
+
+def load_refcvo(calib):
+    """-> RefCvo (a fresh reference cvo object), or None where the reference is not available."""
+    build()
+    if not os.path.exists(LIB_REFCVO):
+        return None
+    if LIB_REFCVO not in _cache:
+        _cache[LIB_REFCVO] = C.CDLL(LIB_REFCVO)
+    return RefCvo(_cache[LIB_REFCVO], calib)

@@ -13,6 +13,18 @@
 #include <cstdint>
 #include <cstring>
 
+// every standard / stand-in header first, so that the access trick below touches the reference's headers only
+#include <complex>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <Eigen/Dense>
+#include <Eigen/Geometry>
+#include <opencv2/opencv.hpp>
+#include <tbb/concurrent_vector.h>
+
 #define private public   // pcd_generator::map / num_want are private; this file only reads / sets them
 #include "pcd_generator.hpp"
 #undef private

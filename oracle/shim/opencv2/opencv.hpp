@@ -10,6 +10,8 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -67,6 +69,32 @@ inline void cvtColor(const Mat &src, Mat &dst, int code) {
         for (int y = 0; y < src.rows; y++) oracle_hsv_u8(src.data + (size_t)y * src.step, src.cols, dst.data + (size_t)y * dst.step);
     }
 }
+// "Key: value" scalars of an OpenCV YAML (cvo.cpp:58-64 reads five)
+struct FileNode {
+    double v = 0;
+    operator float() const { return (float)v; }
+    operator double() const { return v; }
+    operator int() const { return (int)v; }
+};
+class FileStorage {
+    std::string path_;
+public:
+    enum { READ = 0 };
+    FileStorage(const std::string &p, int) : path_(p) {}
+    FileNode operator[](const char *key) const {
+        FileNode n;
+        FILE *f = fopen(path_.c_str(), "r");
+        if (!f) return n;
+        char line[512];
+        const std::string k = std::string(key) + ":";
+        while (fgets(line, sizeof(line), f)) {
+            const char *p = strstr(line, k.c_str());
+            if (p) { n.v = atof(p + k.size()); break; }
+        }
+        fclose(f);
+        return n;
+    }
+};
 // never reached on the selection path (visualize_selected_pixels is commented out of create_pointcloud)
 inline void minMaxLoc(const Mat &, double *mn, double *mx) { if (mn) *mn = 0; if (mx) *mx = 0; }
 inline void applyColorMap(const Mat &, Mat &, int) {}

@@ -1,0 +1,161 @@
+"""Pins of the alignment path against the REFERENCE'S OWN CODE.
+
+tests/golden/refcvo_golden.npz holds outputs of thirdparty/cvo/src/cvo.cpp + LieGroup.cpp (+ the selection sources
+and the vendored nanoflann) compiled where they lie (oracle/Makefile `refcvo`, stand-in Eigen / OpenCV / TBB headers
+under oracle/shim/) — made by tests/golden/make_refcvo_golden.py on the C1 pair.
+
+What the reference's source pins, and how tightly (measured):
+  * cloud sizes, in-cutoff pattern and every a_ij: identical, to the bit;
+  * omega, v of one iteration at an injected state: the reference sums float products per row (cvo.cpp:222-223), the
+    oracle and the CUDA path take the exact sum — they agree to the last float digit or one ulp of the largest
+    component (gate: 2e-6 of the largest component); step: 1e-5 relative;
+  * the free-running loop: bit-identical for the first iterations, then the ulp-level differences above are amplified
+    by the loop itself (a chaotic tail, section 2.1): the reference's own result is only defined up to the basin size,
+    so the gate on the final pose against the reference's free run is the basin (2e-3), while the 1e-4 gate of
+    north_star is applied against the oracle, whose bits the CUDA path reproduces;
+  * inner products and inlier counts at a given transform: equal counts, values to 1e-6; Hessian to 1e-6 of its scale.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pose_error
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("make_refcvo_golden", os.path.join(GOLDEN, "make_refcvo_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def refcvo_golden():
+    return dict(np.load(os.path.join(GOLDEN, "refcvo_golden.npz")))
+
+
+def _check_inputs(g, pair_c1):
+    a, da, b, db, _ = pair_c1
+    crc = [int(x.astype(np.uint64).sum()) for x in (a, da, b, db)]
+    assert crc == [int(x) for x in g["input_crc"]], "the C1 pair is not the one the golden vectors were made from"
+
+
+def _check_backend_against_reference(api, g, pair_c1, tum_calib, bitwise_first_iterations=True):
+    gen = _gen()
+    a, da, b, db, T_gt = pair_c1
+    _check_inputs(g, pair_c1)
+    h = api.create(tum_calib)
+    api.set_frame(h, 0, a, da)
+    api.set_frame(h, 1, b, db)
+    assert [api.slot_size(h, 0), api.slot_size(h, 1)] == g["sizes"].tolist()
+    worst = dict(omega=0.0, v=0.0, step=0.0, bit_equal_flows=0)
+    for s in range(int(g["n_states"])):
+        rec = api.iteration_at(h, g[f"s{s}/R"], g[f"s{s}/T"], float(g[f"s{s}/ell"]))
+        ij, av, n = api.last_pattern(h, 1 << 21)
+        k = gen.keys_of(ij)
+        o = np.argsort(k)
+        assert rec["nnz"] == int(g[f"s{s}/nnz"]) == n, s
+        assert np.array_equal(k[o], g[f"s{s}/keys"]), f"state {s}: in-cutoff pattern differs from the reference's"
+        assert np.array_equal(av[o].view(np.uint32), g[f"s{s}/a"].view(np.uint32)), f"state {s}: a_ij differ in the last bits"
+        for name in ("omega", "v"):
+            ref = g[f"s{s}/{name}"]
+            d = float(np.abs(rec[name] - ref).max() / np.abs(ref).max())
+            worst[name] = max(worst[name], d)
+            assert d < 2e-6, (s, name, rec[name], ref)
+        worst["bit_equal_flows"] += int(np.array_equal(rec["omega"], g[f"s{s}/omega"]) and np.array_equal(rec["v"], g[f"s{s}/v"]))
+        ds = abs(rec["step"] - float(g[f"s{s}/step"])) / float(g[f"s{s}/step"])
+        worst["step"] = max(worst["step"], ds)
+        assert ds < 1e-5, (s, rec["step"], float(g[f"s{s}/step"]))
+    api.destroy(h)
+    # the first iterations of the free-running loop: the same state as the reference's, and what cvo.cpp:815-816
+    # store in prev_transform
+    for k in (1, 2):
+        p = api.default_params()
+        p.max_iter = k
+        h = api.create(tum_calib, p)
+        api.set_frame(h, 0, a, da)
+        api.set_frame(h, 1, b, db)
+        res, _ = api.align(h)
+        if bitwise_first_iterations:
+            assert np.array_equal(res.R_np(), g[f"k{k}/R"]) and np.array_equal(res.T_np(), g[f"k{k}/T"]), k
+            assert np.array_equal(res.transform_np(), g[f"k{k}/transform"]), k
+            assert np.array_equal(res.last_iter_transform_np(), g[f"k{k}/last_iter_transform"]), k
+        else:
+            assert np.allclose(res.transform_np(), g[f"k{k}/transform"], atol=1e-6)
+        assert res.ell == pytest.approx(float(g[f"k{k}/ell"]))
+        api.destroy(h)
+    # free run: same basin as the reference's own free run (see the module docstring), both at the ground truth
+    h = api.create(tum_calib)
+    api.set_frame(h, 0, a, da)
+    api.set_frame(h, 1, b, db)
+    res, _ = api.align(h)
+    ang, dist = pose_error(res.transform_np(), g["free/transform"])
+    assert ang < 2e-3 and dist < 2e-3, (ang, dist)
+    assert res.ell == pytest.approx(float(g["free/ell"]))
+    ang_gt, dist_gt = pose_error(g["free/transform"], T_gt)
+    assert ang_gt < 5e-3 and dist_gt < 5e-3
+    # compute_innerproduct at the reference's final transform and ell
+    api.set_ell(h, float(g["free/ell"]))
+    T = g["free/transform"]
+    vals = [api.inner_product(h, 1, None, 0), api.inner_product(h, 1, T, 0), api.inner_product(h, 0, None, 0),
+            api.inner_product(h, 1, None, 1)]
+    for (v, n), gv, gn in zip(vals, g["free/inn_values"], g["free/inn_nums"]):
+        assert n == int(gn)
+        assert v == pytest.approx(float(gv), rel=1e-6)
+    H, inl = api.hessian(h, 1, T, 0)
+    assert inl == int(g["free/inliers"])
+    assert np.allclose(H, g["free/H"], rtol=0, atol=1e-6 * np.abs(g["free/H"]).max())
+    api.destroy(h)
+    return worst, (ang, dist)
+
+
+def test_oracle_matches_reference_cvo_golden(oracle_api, refcvo_golden, pair_c1, tum_calib):
+    worst, basin = _check_backend_against_reference(oracle_api, refcvo_golden, pair_c1, tum_calib)
+    print("oracle vs the reference's cvo.cpp: worst relative flow difference", worst, "free-run pose difference", basin)
+
+
+def test_reference_cvo_live(oracle_api, pair_c1, tum_calib):
+    """Where /root/reference is present: the compiled reference class run live — state persistence over two
+    alignments (R, T, ell left behind; update_fixed_pcd), reset_initial, and one more pair than the golden file."""
+    from oracle import oracle
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    rc = oracle.load_refcvo(tum_calib)
+    if rc is None:
+        pytest.skip("oracle/_ref/libref_cvo.so not built (no /root/reference here)")
+    a, da, b, db, _ = synth.make_pair(7, tum_calib, rot_deg=0.8, trans=(0.015, -0.01, 0.012))
+    rc.set_pcd(a, da)
+    rc.set_pcd(b, db)
+    c = cvo_mod.Cvo(tum_calib, api=oracle_api)
+    c.set_pcd(a, da)
+    c.set_pcd(b, db)
+    assert rc.sizes() == c.get_fixed_and_moving_number()
+    # reset_initial (cvo.cpp:611-618): the prior lands in R, T; the returned inverse
+    odom = synth.pose((0.004, -0.003, 0.002), (0.01, 0.004, -0.006)).astype(np.float32)
+    back_r = rc.reset_initial(odom)
+    back_o = c.reset_initial(odom)
+    Rr, Tr, ellr, _ = rc.get_state()
+    Ro, To = oracle_api.get_RT(c.h)
+    assert np.array_equal(Rr, Ro) and np.array_equal(Tr, To) and np.array_equal(back_r, back_o)
+    # one iteration from that prior: same bits in the pattern, flows to 2e-6
+    r1 = rc.iteration_at(Rr, Tr, 0.15)
+    o1 = oracle_api.iteration_at(c.h, Ro, To, 0.15)
+    assert r1["nnz"] == o1["nnz"]
+    for name in ("omega", "v"):
+        assert np.abs(r1[name] - o1[name]).max() / np.abs(o1[name]).max() < 2e-6
+    assert r1["step"] == pytest.approx(o1["step"], rel=1e-5)
+    # two alignments in a row on the same objects: ell / R / T persist in both
+    ra = rc.align()
+    c.align()
+    assert ra["ell"] == pytest.approx(oracle_api.get_ell(c.h))
+    ang, dist = pose_error(ra["transform"], c.transform)
+    assert ang < 2e-3 and dist < 2e-3
+    rc.close()
+    c.close()
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_cvo_golden(cuda_api, refcvo_golden, pair_c1, tum_calib):
+    worst, basin = _check_backend_against_reference(cuda_api, refcvo_golden, pair_c1, tum_calib)
+    print("CUDA vs the reference's cvo.cpp: worst relative flow difference", worst, "free-run pose difference", basin)
