@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("CVO_B200_OUT") or os.path.join(HERE, "libcvo_b200.so")
 # align.cu is compiled with -fmad=false: every float/double operation of the alignment loop must
 # round exactly as the oracle's (no FMA contraction); its hot loops use explicit _rn intrinsics.
-SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": [], "multi.cu": []}
+SOURCES = {"select.cu": [], "align.cu": ["-fmad=false"], "capi.cu": [], "multi.cu": [], "ingest.cu": []}
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "cvo_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -45,7 +45,7 @@ def build(force=False, verbose=False, extra=()):
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lz"]   # zlib: DEFLATE of the PNG ingest
     if verbose:
         print(" ".join(link))
     subprocess.check_call(link, env=env)

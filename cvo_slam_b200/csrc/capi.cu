@@ -14,6 +14,7 @@
 
 #include <map>
 #include <utility>
+#include <thread>
 #include <vector>
 
 namespace cvo_b200 {
@@ -65,6 +66,12 @@ struct cvo_handle {
     int slot_idx[3] = {-1, -1, -1};
     SelWorkspace *sel = nullptr;
     int sel_w = 0, sel_h = 0, sel_slot = -1;
+    // pinned frame staging of cvo_set_frame_png: two buffers alternate, an event per buffer marks "H2D done"
+    uint8_t *png_bgr[2] = {nullptr, nullptr};
+    uint16_t *png_depth[2] = {nullptr, nullptr};
+    cudaEvent_t png_done[2] = {nullptr, nullptr};
+    size_t png_px = 0;
+    int png_next = 0;
     AlignWorkspace *aws = nullptr;
     float R[9], T[3], ell;
     // device + pinned staging
@@ -253,6 +260,11 @@ int cvo_destroy(cvo_handle *h) {
     if (h->arena.pos) arena_free(h->arena);
     cudaFree(h->d_task); cudaFree(h->d_res); cudaFree(h->d_trace); cudaFree(h->d_q); cudaFree(h->d_qo);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int i = 0; i < 2; i++) {
+        if (h->png_bgr[i]) cudaFreeHost(h->png_bgr[i]);
+        if (h->png_depth[i]) cudaFreeHost(h->png_depth[i]);
+        if (h->png_done[i]) cudaEventDestroy(h->png_done[i]);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CVO_OK;
@@ -289,6 +301,51 @@ int cvo_set_frame(cvo_handle *h, int slot, const uint8_t *bgr, size_t bgr_stride
     rc = sel_run(h->sel, 1, nullptr, nullptr, h->cal, h->prm, h->arena, k, h->stream, &h->launches);
     h->sel_slot = slot;
     return rc;
+}
+
+// run_SLAM.cpp:134-143 + cvo::set_pcd in one call: the colour PNG (-> BGR8, as cv::imread) and the depth PNG
+// (-> u16, as cv::imread with ANYDEPTH) are decoded on two host threads straight into pinned staging memory, then
+// uploaded and selected on the handle's stream.  Two staging buffers alternate, so the decode of the next frame may
+// start while the copy of this one is still in flight.
+int cvo_set_frame_png(cvo_handle *h, int slot, const uint8_t *rgb_png, size_t rgb_bytes, const uint8_t *depth_png,
+                      size_t depth_bytes) {
+    if (!h || !slot_ok(slot) || !rgb_png || !depth_png) return CVO_ERR_INVALID;
+    int w = 0, hgt = 0, wd = 0, hd = 0, ch = 0, bits = 0;
+    int rc = cvo_png_info(rgb_png, rgb_bytes, &w, &hgt, &ch, &bits);
+    if (rc == CVO_OK) rc = cvo_png_info(depth_png, depth_bytes, &wd, &hd, &ch, &bits);
+    if (rc != CVO_OK) return rc;
+    if (w != wd || hgt != hd) { set_last_error("cvo_set_frame_png: colour is %d x %d, depth %d x %d", w, hgt, wd, hd); return CVO_ERR_INVALID; }
+    CVO_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t px = (size_t)w * hgt;
+    if (h->png_px != px) {
+        CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 2; i++) {
+            if (h->png_bgr[i]) cudaFreeHost(h->png_bgr[i]);
+            if (h->png_depth[i]) cudaFreeHost(h->png_depth[i]);
+            h->png_bgr[i] = nullptr; h->png_depth[i] = nullptr;
+            CVO_CUDA_TRY(cudaMallocHost(&h->png_bgr[i], px * 3));
+            CVO_CUDA_TRY(cudaMallocHost(&h->png_depth[i], px * 2));
+            if (!h->png_done[i]) CVO_CUDA_TRY(cudaEventCreateWithFlags(&h->png_done[i], cudaEventDisableTiming));
+        }
+        h->png_px = px;
+    }
+    const int b = h->png_next;
+    h->png_next ^= 1;
+    CVO_CUDA_TRY(cudaEventSynchronize(h->png_done[b]));   // the copy that last read this buffer has finished
+    int rc_d = CVO_OK;
+    char err_d[256] = "";
+    std::thread td([&] {
+        rc_d = cvo_png_decode_depth16(depth_png, depth_bytes, h->png_depth[b], px, nullptr, nullptr);
+        if (rc_d != CVO_OK) { strncpy(err_d, cvo_last_error(), sizeof(err_d) - 1); }
+    });
+    rc = cvo_png_decode_bgr8(rgb_png, rgb_bytes, h->png_bgr[b], px * 3, nullptr, nullptr);
+    td.join();
+    if (rc == CVO_OK && rc_d != CVO_OK) { set_last_error("%s", err_d); rc = rc_d; }
+    if (rc != CVO_OK) return rc;
+    rc = cvo_set_frame(h, slot, h->png_bgr[b], (size_t)w * 3, h->png_depth[b], (size_t)w * 2, w, hgt);
+    if (rc != CVO_OK) return rc;
+    CVO_CUDA_TRY(cudaEventRecord(h->png_done[b], h->stream));
+    return CVO_OK;
 }
 
 int cvo_set_frame_device(cvo_handle *h, int slot, const uint8_t *bgr_dev, const uint16_t *depth_dev, int width,

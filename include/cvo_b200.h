@@ -242,6 +242,28 @@ int cvo_batch_last_align_ms(cvo_batch *b, float *ms);
 int cvo_batch_mark(cvo_batch *b, int which);
 int cvo_batch_elapsed_ms(cvo_batch *b, float *ms);
 
+/* ---- image ingest (src/run_SLAM.cpp:134-143: cv::imread of the colour and the depth PNG) ------------------------
+ * cvo_png_decode_bgr8 produces the buffer cv::imread(path) returns for an 8/16-bit gray / RGB / RGBA PNG (8-bit,
+ * 3 channels, B G R); cvo_png_decode_depth16 the buffer cv::imread(path, CV_LOAD_IMAGE_ANYDEPTH) returns for a 16-bit
+ * gray PNG (u16, host byte order).  out may be NULL to query the size only.  Non-interlaced, non-palette files. */
+int cvo_png_info(const uint8_t *png, size_t n, int *width, int *height, int *channels, int *bit_depth);
+int cvo_png_decode_bgr8(const uint8_t *png, size_t n, uint8_t *out, size_t out_bytes, int *width, int *height);
+int cvo_png_decode_depth16(const uint8_t *png, size_t n, uint16_t *out, size_t out_elems, int *width, int *height);
+/* imread x 2 + cvo::set_pcd in one call: both PNGs decoded in parallel into pinned staging, then cvo_set_frame */
+int cvo_set_frame_png(cvo_handle *h, int slot, const uint8_t *rgb_png, size_t rgb_bytes,
+                      const uint8_t *depth_png, size_t depth_bytes);
+/* A decode prefetcher: n_threads workers decode submitted frames, in order, into a ring of n_slots pinned frames while
+ * the caller aligns the previous ones.  submit copies the PNG bytes and returns (blocks only when the ring is full);
+ * wait returns the oldest frame's pinned BGR8 / u16 buffers (ready for cvo_set_frame: the H2D copy from pinned memory
+ * is asynchronous); release hands the slot back. */
+typedef struct cvo_ingest cvo_ingest;
+int cvo_ingest_create(int width, int height, int n_slots, int n_threads, cvo_ingest **out);
+int cvo_ingest_destroy(cvo_ingest *g);
+int cvo_ingest_submit(cvo_ingest *g, const uint8_t *rgb_png, size_t rgb_bytes, const uint8_t *depth_png,
+                      size_t depth_bytes);
+int cvo_ingest_wait(cvo_ingest *g, const uint8_t **bgr, const uint16_t **depth, int *width, int *height);
+int cvo_ingest_release(cvo_ingest *g);
+
 /* ---- one list of frames and pairs over several GPUs of this process ----------------------------
  * SURVEY section 8b lists a batch entry with an n_devices argument: the candidate loop of
  * src/keyframe_graph.cpp:622-731 with the pairs split into n_devices contiguous blocks (section 8e: pairs

@@ -13,7 +13,8 @@ What the reference's source pins, and how tightly (measured, DESIGN.md section 2
     by the loop itself (a chaotic tail, section 2.1): the reference's own result is only defined up to the basin size,
     so the gate on the final pose against the reference's free run is the basin (2e-3), while the 1e-4 gate of
     north_star is applied against the oracle, whose bits the CUDA path reproduces;
-  * inner products and inlier counts at a given transform: equal counts, values to 1e-6; Hessian to 1e-6 of its scale.
+  * inner products and inlier counts at a given transform: equal counts; values and Hessian to 1e-6 (of its scale) for
+    the oracle, to north_star's 1e-4 for the CUDA queries, which use MUFU ex2 (observed ~1e-6).
 """
 import importlib.util
 import os
@@ -42,7 +43,7 @@ def _check_inputs(g, pair_c1):
     assert crc == [int(x) for x in g["input_crc"]], "the C1 pair is not the one the golden vectors were made from"
 
 
-def _check_backend_against_reference(api, g, pair_c1, tum_calib, bitwise_first_iterations=True):
+def _check_backend_against_reference(api, g, pair_c1, tum_calib, bitwise_first_iterations=True, query_rtol=1e-6):
     gen = _gen()
     a, da, b, db, T_gt = pair_c1
     _check_inputs(g, pair_c1)
@@ -103,10 +104,10 @@ def _check_backend_against_reference(api, g, pair_c1, tum_calib, bitwise_first_i
             api.inner_product(h, 1, None, 1)]
     for (v, n), gv, gn in zip(vals, g["free/inn_values"], g["free/inn_nums"]):
         assert n == int(gn)
-        assert v == pytest.approx(float(gv), rel=1e-6)
+        assert v == pytest.approx(float(gv), rel=query_rtol)
     H, inl = api.hessian(h, 1, T, 0)
     assert inl == int(g["free/inliers"])
-    assert np.allclose(H, g["free/H"], rtol=0, atol=1e-6 * np.abs(g["free/H"]).max())
+    assert np.allclose(H, g["free/H"], rtol=0, atol=query_rtol * np.abs(g["free/H"]).max())
     api.destroy(h)
     return worst, (ang, dist)
 
@@ -157,5 +158,6 @@ def test_reference_cvo_live(oracle_api, pair_c1, tum_calib):
 
 @pytest.mark.gpu
 def test_cuda_matches_reference_cvo_golden(cuda_api, refcvo_golden, pair_c1, tum_calib):
-    worst, basin = _check_backend_against_reference(cuda_api, refcvo_golden, pair_c1, tum_calib)
+    # the CUDA queries evaluate their exponentials with MUFU ex2 (north_star: inner products within 1e-4 relative)
+    worst, basin = _check_backend_against_reference(cuda_api, refcvo_golden, pair_c1, tum_calib, query_rtol=1e-4)
     print("CUDA vs the reference's cvo.cpp: worst relative flow difference", worst, "free-run pose difference", basin)
