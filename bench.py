@@ -239,7 +239,7 @@ def measured_hbm_peak():
         return 6549.0, "fallback: 6549 GB/s (the pool's measured copy bandwidth at the time of writing)"
 
 
-def cpp_sequence(frames, T_kf_last_python):
+def cpp_sequence(frames, T_kf_last_python, dedup=False):
     """Compiles scripts/seq_dropin.cpp against include/cvo.hpp + libcvo_b200.so and runs it on `frames`
     (list of (bgr, depth) arrays).  -> dict(ms_per_frame, passes, same_bits) or None."""
     from cvo_slam_b200 import capi
@@ -258,7 +258,7 @@ def cpp_sequence(frames, T_kf_last_python):
                 f.write("%YAML:1.0\nCamera.fx: 517.306408\nCamera.fy: 516.469215\nCamera.cx: 318.643040\n"
                         "Camera.cy: 255.313989\nDepthMapFactor: 5000.0\n")
             out = subprocess.run([exe, calib, os.path.join(td, "bgr.raw"), os.path.join(td, "depth.raw"),
-                                  str(len(frames)), str(W), str(H), "3"], check=True, capture_output=True, text=True).stdout
+                                  str(len(frames)), str(W), str(H), "3", "1" if dedup else "0"], check=True, capture_output=True, text=True).stdout
         tok = out.split()
         i = tok.index("ms_per_frame")
         j = tok.index("T_kf_last")
@@ -311,6 +311,10 @@ def sequence_leg(n_frames, api, device, cpu_frames=6):
                    frames_per_s=1e3 / cpp["ms_per_frame"],
                    alignments_per_s=(2 * (n_frames - 1) - 1) / ((n_frames - 1) * cpp["ms_per_frame"] * 1e-3),
                    cpp_matches_python_bits=cpp["same_bits"])
+        dd = cpp_sequence(frames, out[-1]["keyframe"], dedup=True)
+        if dd:   # opt-in de-duplicated front end: one selection per frame instead of two
+            res["dedup_front_end"] = dict(ms_per_frame=dd["ms_per_frame"], frames_per_s=1e3 / dd["ms_per_frame"],
+                                          same_bits_as_two_selections=dd["same_bits"])
     else:
         res["host"] = "Python ctypes mirror of the class (cvo_slam_b200/cvo.py); the C++ runner could not be built here"
     if cpu_frames:

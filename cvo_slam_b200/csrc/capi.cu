@@ -693,6 +693,19 @@ int cvo_get_cloud(cvo_handle *h, int slot, float *positions, float *features, in
     return CVO_OK;
 }
 
+// Keyframe re-does the gray conversion of the image the CVO front end has just converted
+// (include/keyframe.h:34-55).  The selection keeps the gray image of the LAST frame set on this handle on the device.
+int cvo_get_gray_device(cvo_handle *h, int slot, const uint8_t **gray_dev, int *width, int *height) {
+    if (!h || !slot_ok(slot) || !gray_dev) return CVO_ERR_INVALID;
+    if (!h->sel || h->sel_slot != slot) return CVO_ERR_NOT_INIT;   // only the last selected frame is kept
+    CVO_CUDA_TRY(cudaSetDevice(h->device));
+    CVO_CUDA_TRY(cudaStreamSynchronize(h->stream));   // work queued on the handle's stream has completed
+    *gray_dev = sel_gray_ptr(h->sel, 0);
+    if (width) *width = h->sel_w;
+    if (height) *height = h->sel_h;
+    return CVO_OK;
+}
+
 int cvo_get_selection_debug(cvo_handle *h, int slot, uint8_t *map, int32_t info[5]) {
     if (!h || !slot_ok(slot) || !info) return CVO_ERR_INVALID;
     if (!h->sel || h->sel_slot != slot) return CVO_ERR_NOT_INIT;   // only the last selected frame is kept

@@ -82,6 +82,7 @@ int sel_run(SelWorkspace *ws, int n, const uint8_t *bgr_dev, const uint16_t *dep
             cudaStream_t stream, int64_t *launch_counter);
 // debug: status map (after sub-sampling) and {n2,n3,n4,pot,passes} of chunk-local frame k
 int sel_debug(SelWorkspace *ws, int k, uint8_t *map_host, int32_t info[5], cudaStream_t stream);
+const uint8_t *sel_gray_ptr(const SelWorkspace *ws, int k);   // device gray image of chunk-local frame k (tightly packed rows)
 void host_random_pattern(uint8_t *out, int n);
 
 // ---- alignment (align.cu) -----------------------------------------------------------------------

@@ -633,6 +633,12 @@ int sel_run(SelWorkspace *ws, int n, const uint8_t *bgr_dev, const uint16_t *dep
     return CVO_OK;
 }
 
+// the 8-bit gray image (cv::cvtColor RGB2GRAY, row A) of chunk-local frame k as the selection left it on the device
+const uint8_t *sel_gray_ptr(const SelWorkspace *ws, int k) {
+    if (!ws || k < 0 || k >= ws->chunk) return nullptr;
+    return ws->d.gray + (size_t)k * ws->d.npx_pad;
+}
+
 int sel_debug(SelWorkspace *ws, int k, uint8_t *map_host, int32_t info[5], cudaStream_t stream) {
     if (k < 0 || k >= ws->chunk) return CVO_ERR_INVALID;
     SelState st;

@@ -107,6 +107,25 @@ class Cvo:
         self._sizes_valid = False     # the reference refreshes num_fixed / num_moving here (cvo.cpp:370-371)
         self.A_nonzero = 0
 
+    def set_pcd_from(self, src, src_slot):
+        """Opt-in (include/cvo.hpp set_pcd_from): adopt the device cloud `src` has just selected for
+        the same image instead of selecting it again."""
+        slot = SLOT_MOVING if self.init else SLOT_FIXED
+        self.api.copy_cloud(self.h, slot, src.h, src_slot)
+        if not self.init:
+            self.init = True
+            return
+        self._sizes_valid = False
+        self.A_nonzero = 0
+
+    def match_keyframe_from(self, src, src_slot):
+        if not self.init:
+            print("cvo not initialized !")
+            return None
+        self.set_pcd_from(src, src_slot)
+        self.align()
+        return self.transform.astype(np.float64)
+
     # ---- cvo.cpp:763-821 -------------------------------------------------------------------
     def align(self, trace_cap=0):
         res, recs = self.api.align(self.h, trace_cap)
@@ -238,18 +257,23 @@ class Cvo:
         return self.api.get_selected_points(self.h, SLOT_MOVING)
 
 
-def track_sequence(frames, calib, params=None, api=None, device=0):
+def track_sequence(frames, calib, params=None, api=None, device=0, dedup=False):
     """The per-frame call pattern of LocalTracker (src/local_tracker.cpp:223-251, 349-431) with two
     cvo objects (consecutive-frame odometry and keyframe tracking).  Keyframes are never
     replaced here (the keyframe decision lives in KeyframeTracker, out of scope); the first
-    frame is the keyframe.  `frames` is a list of (bgr, depth).  Returns per-frame dicts."""
+    frame is the keyframe.  `frames` is a list of (bgr, depth).  Returns per-frame dicts.
+    dedup: the keyframe object adopts the cloud the odometry object selected for the same image
+    (set_pcd_from / match_keyframe_from) instead of selecting it again (CUDA library only)."""
     odo = Cvo(calib, params, api, device)
     kf = Cvo(calib, params, api, device)
     out = []
     # initNewLocalMap (local_tracker.cpp:223-345): both objects take the keyframe, odometry
     # aligns the second frame, the keyframe object adopts the odometry transform
     odo.set_pcd(*frames[0])
-    kf.set_pcd(*frames[0])
+    if dedup:
+        kf.set_pcd_from(odo, SLOT_FIXED)
+    else:
+        kf.set_pcd(*frames[0])
     T = odo.match_odometry(*frames[1])
     r = odo.compute_innerproduct(T.astype(np.float32))
     kf.first_frame = False
@@ -261,7 +285,7 @@ def track_sequence(frames, calib, params=None, api=None, device=0):
         r_odo = odo.compute_innerproduct(T_odo.astype(np.float32))
         odo.update_fixed_pcd()
         kf.reset_initial(T_odo.astype(np.float32))
-        T_kf = kf.match_keyframe(rgb, dep)
+        T_kf = kf.match_keyframe_from(odo, SLOT_FIXED) if dedup else kf.match_keyframe(rgb, dep)
         r_kf = kf.compute_innerproduct(T_kf.astype(np.float32))
         kf.update_previous_pcd()   # accepted frame (local_tracker.cpp:506)
         out.append(dict(odometry=T_odo, keyframe=T_kf, r_odometry=r_odo, r_keyframe=r_kf))

@@ -333,6 +333,25 @@ public:
         detail::from_rows(r.transform, transform);
     }
 
+    /* Opt-in, not in the reference: LocalTracker hands the SAME image to its two cvo objects
+     * (local_tracker.cpp:356,415), so the reference selects its points twice per frame.  A caller that knows this lets
+     * the second object adopt the cloud the first one has just selected: set_pcd_from(src, slot) is set_pcd with the
+     * device cloud of `src`'s slot (CVO_SLOT_MOVING before src.update_fixed_pcd(), CVO_SLOT_FIXED after it) in place
+     * of the images; match_keyframe_from is match_keyframe on it.  Same clouds, same bits downstream. */
+    void set_pcd_from(cvo &src, int src_slot) {
+        const int slot = init ? CVO_SLOT_MOVING : CVO_SLOT_FIXED;
+        check(cvo_copy_cloud(h_, slot, src.h_, src_slot), "cvo_copy_cloud");
+        if (!init) { init = true; return; }
+        sizes_valid_ = false;
+        A_nonzero = 0;
+    }
+    void match_keyframe_from(cvo &src, int src_slot, affine3d_t &transformd) {
+        if (init == false) { std::cout << "cvo not initialized !" << "\n"; return; }
+        set_pcd_from(src, src_slot);
+        align();
+        transformd = transform.template cast<double>();
+    }
+
     /* cvo.cpp:461-473 */
     void match_odometry(const mat_t &RGB_img, const mat_t &dep_img, affine3d_t &transformd) {
         if (init == false) { std::cout << "cvo not initialized !" << "\n"; return; }

@@ -185,6 +185,11 @@ int cvo_get_selected_points(cvo_handle *h, int slot, float *xy, int cap, int *n)
  * n (x, y) float pairs in raster order, valid until the slot is overwritten or moved; work queued on
  * the handle's stream has completed when the call returns. */
 int cvo_get_selected_points_device(cvo_handle *h, int slot, const float **xy_dev, int *n);
+/* the 8-bit gray image of the frame most recently set on `slot` (RGB2GRAY as pcd_generator::load_image computes it,
+ * pcd_generator.cpp:624), width x height bytes, tightly packed, on the device: the ORB side (include/keyframe.h:34-55)
+ * converts the same image again on the host.  Valid until the next cvo_set_frame* on this handle; CVO_ERR_NOT_INIT
+ * when another slot was set last. */
+int cvo_get_gray_device(cvo_handle *h, int slot, const uint8_t **gray_dev, int *width, int *height);
 /* positions n x 3, features n x 5 row-major (tests, and host point_cloud mirrors) */
 int cvo_get_cloud(cvo_handle *h, int slot, float *positions, float *features, int cap, int *n);
 /* selector internals for the bit-exactness tests: status map (w*h bytes, 0/1/2/4 after

@@ -1,7 +1,8 @@
 // C2 through the drop-in C++ class (include/cvo.hpp): the per-frame call pattern of LocalTracker
 // (src/local_tracker.cpp:223-251, 349-431) with two cvo::cvo objects — consecutive-frame odometry and
 // keyframe tracking — on a sequence of raw frames, timed on the host like the reference's own loop.
-// usage: seq_dropin calib.yaml bgr.raw depth.raw N W H [passes]
+// usage: seq_dropin calib.yaml bgr.raw depth.raw N W H [passes] [dedup]
+//   dedup = 1: the keyframe object adopts the odometry object's selection of the same image (cvo::set_pcd_from)
 //   bgr.raw = N x H x W x 3 bytes, depth.raw = N x H x W x 2 bytes (uint16).
 // prints one line:  frames N passes P ms_per_frame <p0> <p1> ... T_kf_last <16 floats>
 #include <chrono>
@@ -27,6 +28,7 @@ int main(int argc, char **argv) {
     if (argc < 7) { fprintf(stderr, "usage: %s calib.yaml bgr.raw depth.raw N W H [passes]\n", argv[0]); return 1; }
     const int N = atoi(argv[4]), W = atoi(argv[5]), H = atoi(argv[6]);
     const int passes = argc > 7 ? atoi(argv[7]) : 3;
+    const bool dedup = argc > 8 && atoi(argv[8]) != 0;
     std::vector<unsigned char> bgr = slurp(argv[2]), dep = slurp(argv[3]);
     if (bgr.size() != (size_t)N * W * H * 3 || dep.size() != (size_t)N * W * H * 2 || N < 3) return 4;
     auto img = [&](int k, cvo::mat_t &c, cvo::mat_t &d) {
@@ -48,7 +50,8 @@ int main(int argc, char **argv) {
         // initNewLocalMap (local_tracker.cpp:223-345)
         img(0, c, d);
         odo.set_pcd(c, d);
-        kf.set_pcd(c, d);
+        if (dedup) kf.set_pcd_from(odo, CVO_SLOT_FIXED);
+        else kf.set_pcd(c, d);
         cvo::affine3d_t T;
         img(1, c, d);
         odo.match_odometry(c, d, T);
@@ -65,7 +68,8 @@ int main(int argc, char **argv) {
             odo.compute_innerproduct(pre, post, Hm, To, inliers, fx, mv, cosang);
             odo.update_fixed_pcd();
             kf.reset_initial(To);
-            kf.match_keyframe(c, d, T_kf);
+            if (dedup) kf.match_keyframe_from(odo, CVO_SLOT_FIXED, T_kf);
+            else kf.match_keyframe(c, d, T_kf);
             cvo::affine3f_t Tk = T_kf.cast<float>();
             kf.compute_innerproduct(pre, post, Hm, Tk, inliers, fx, mv, cosang);
             kf.update_previous_pcd();   // accepted frame (local_tracker.cpp:506)

@@ -516,6 +516,30 @@ def test_tracking_sequence_c2_300_frames(cuda_api, oracle_api, tum_calib):
           "max keyframe error vs ground truth", max(e[0] for e in gt_err), max(e[1] for e in gt_err))
 
 
+def test_dedup_front_end_matches_oracle(cuda_api, oracle_api, tum_calib):
+    """the keyframe object adopts the odometry object's selection of the same image
+    (cvo::set_pcd_from / match_keyframe_from over cvo_copy_cloud) — checked against the ORACLE driven the reference's
+    way (two selections per frame), not against a second CUDA handle."""
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    scene = synth.make_scene(2)
+    poses = synth.trajectory(10, 2)
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=20 + k))
+              for k, P in enumerate(poses)]
+    out_c = cvo_mod.track_sequence(frames, tum_calib, api=cuda_api, dedup=True)
+    out_o = cvo_mod.track_sequence(frames, tum_calib, api=oracle_api)
+    for k, (c, o) in enumerate(zip(out_c, out_o)):
+        for key in ("odometry", "keyframe"):
+            ang, dist = pose_error(c[key], o[key])
+            assert ang < POSE_TOL_RAD and dist < POSE_TOL_M, (k, key, ang, dist)
+        for rk in ("r_odometry", "r_keyframe"):
+            for key in ("inn_pre", "inn_post", "inn_fixed_pcd", "inn_moving_pcd"):
+                assert c[rk][key].num == o[rk][key].num
+                assert float(c[rk][key].value) == pytest.approx(float(o[rk][key].value), rel=INNER_RTOL)
+    # and bit-identical to the CUDA path that selects twice
+    out_2 = cvo_mod.track_sequence(frames, tum_calib, api=cuda_api)
+    assert all(np.array_equal(a["keyframe"], b["keyframe"]) for a, b in zip(out_c, out_2))
+
+
 def test_cpp_dropin_matches_python_path(cuda_api, tum_calib, pair_c1, tmp_path):
     """The C++ drop-in class (include/cvo.hpp) driven like LocalTracker gives the same bits as the
     ctypes path: same library, same kernels."""
@@ -851,6 +875,16 @@ def test_selected_points_device_pointer(cuda_api, tum_calib, pair_c1):
     out = np.zeros((n, 2), np.float32)
     assert rt.cudaMemcpy(out.ctypes.data, ptr, n * 8, 2) == 0   # cudaMemcpyDeviceToHost
     assert np.array_equal(out, host)
+    # the device gray image of the same frame (what Keyframe recomputes with cv::cvtColor, include/keyframe.h:34-55)
+    gp, w, hh = C.c_void_p(), C.c_int(0), C.c_int(0)
+    cuda_api.lib.cvo_get_gray_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    assert cuda_api.lib.cvo_get_gray_device(h, 0, C.byref(gp), C.byref(w), C.byref(hh)) == 0
+    assert (w.value, hh.value) == (640, 480)
+    gray = np.zeros((480, 640), np.uint8)
+    assert rt.cudaMemcpy(gray.ctypes.data, gp, gray.size, 2) == 0
+    cv2 = pytest.importorskip("cv2")
+    assert np.array_equal(gray, cv2.cvtColor(bgr_a, cv2.COLOR_RGB2GRAY))
+    assert cuda_api.lib.cvo_get_gray_device(h, 1, C.byref(gp), None, None) == -3   # nothing set on that slot last
     cuda_api.destroy(h)
 
 
