@@ -17,6 +17,8 @@
 
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -381,6 +383,28 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *warp_tot, int *t
     return res;
 }
 
+// The same scan across the kCompactCtas CTAs of a thread-block cluster (one cluster per frame): block scan, the
+// CTA totals are exchanged through distributed shared memory.  `xch` is a per-CTA shared slot (one per call site,
+// so that a slot is never rewritten while a slower peer still reads it).
+constexpr int kCompactCtas = 8;
+__device__ __forceinline__ int cluster_exclusive_scan(int v, int *warp_tot, int *xch, int *total) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    int cta_total;
+    const int local = block_exclusive_scan(v, warp_tot, &cta_total);
+    if (threadIdx.x == 0) *xch = cta_total;
+    cl.sync();
+    int before = 0, all = 0;
+    const unsigned me = cl.block_rank();
+    for (unsigned r = 0; r < cl.num_blocks(); r++) {
+        const int t = *cl.map_shared_rank(xch, r);
+        if (r < me) before += t;
+        all += t;
+    }
+    *total = all;
+    return before + local;
+}
+
 struct ArenaDev {
     float4 *pos;
     float4 *f03;
@@ -397,7 +421,11 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
                                                   size_t depth_stride) {
     __shared__ int warp_tot[33];
     __shared__ int s_use_b, s_sub, s_charTH;
-    const int f = blockIdx.x;
+    __shared__ int s_xch[3];   // CTA totals of the three scans, read by the peers of the cluster
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int crank = (int)cl.block_rank(), csize = (int)cl.num_blocks();
+    const int f = blockIdx.x / csize;   // one cluster per frame: 8 x 1024 threads share the raster scan
     SelState *st = d.st + f;
     if (threadIdx.x == 0) {
         int need2, pot2;
@@ -407,11 +435,13 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
         float quotia = __fdiv_rn(d.num_want, numHave);
         int sub = (double)quotia < 0.95;
         int charTH = sub ? (int)(unsigned char)__fmul_rn(255.f, quotia) : 255;
-        st->need2 = need2;
-        st->pot2 = pot2;
-        st->use_b = need2;
-        st->subsample = sub;
-        st->charTH = charTH;
+        if (crank == 0) {   // (every CTA of the cluster derives the same decision; one stores it)
+            st->need2 = need2;
+            st->pot2 = pot2;
+            st->use_b = need2;
+            st->subsample = sub;
+            st->charTH = charTH;
+        }
         s_use_b = need2;
         s_sub = sub;
         s_charTH = charTH;
@@ -421,8 +451,9 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
     const uint32_t *map32 = reinterpret_cast<const uint32_t *>(map);
     const int sub = s_sub, charTH = s_charTH;
     const int nwords = d.npx_pad / 4;
-    const int per = (nwords + blockDim.x - 1) / blockDim.x;
-    const int w0 = min((int)threadIdx.x * per, nwords), w1 = min(w0 + per, nwords);
+    const int nthr = (int)blockDim.x * csize, gthr = crank * (int)blockDim.x + (int)threadIdx.x;
+    const int per = (nwords + nthr - 1) / nthr;
+    const int w0 = min(gthr * per, nwords), w1 = min(w0 + per, nwords);
     const uint16_t *dep = depth + (size_t)f * depth_stride;
     const uint8_t *img = bgr + (size_t)f * bgr_stride;
     const uint8_t *gray = d.gray + (size_t)f * d.npx_pad;
@@ -431,7 +462,7 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
     int c = 0;
     for (int k = w0; k < w1; k++) c += __popc(__vcmpne4(map32[k], 0u)) >> 3;
     int total_sel;
-    const int rn0 = block_exclusive_scan(c, warp_tot, &total_sel);
+    const int rn0 = cluster_exclusive_scan(c, warp_tot, &s_xch[0], &total_sel);
 
     // pass 2: apply randomPattern[rn] > charTH removal and the depth filter; count survivors
     int rn = rn0, kept = 0, kept_sub = 0;
@@ -450,8 +481,8 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
     }
     __syncthreads();
     int total_sub, total_out;
-    block_exclusive_scan(kept_sub, warp_tot, &total_sub);
-    const int out0 = block_exclusive_scan(kept, warp_tot, &total_out);
+    cluster_exclusive_scan(kept_sub, warp_tot, &s_xch[1], &total_sub);
+    const int out0 = cluster_exclusive_scan(kept, warp_tot, &s_xch[2], &total_out);
 
     // pass 3: survivors in raster order -> position, pixel, features
     const size_t base = (size_t)(A.first + f) * A.cap;
@@ -504,13 +535,14 @@ __global__ void __launch_bounds__(1024) k_compact(SelDev d, ArenaDev A, const ui
             o++;
         }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && crank == 0) {
         st->n_selected = total_sub;
         st->n_out = total_out;
         st->overflow = total_out > A.cap;
         A.n[A.first + f] = min(total_out, A.cap);
         A.ovf[A.first + f] = total_out > A.cap ? 1 : 0;   // surfaces as CVO_ERR_CAPACITY / CVO_ERR_PAIR_OVERFLOW downstream
     }
+    cl.sync();   // no CTA leaves while a peer may still read its scan totals
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,7 +659,21 @@ int sel_run(SelWorkspace *ws, int n, const uint8_t *bgr_dev, const uint16_t *dep
         k_select<<<dim3((tiles * 16 + 255) / 256, fn), 256, 0, stream>>>(d, 1);
     }
     ArenaDev A{arena.pos, arena.f03, arena.f4, arena.pix, arena.n, arena.ovf, arena.cap, first};
-    k_compact<<<fn, 1024, 0, stream>>>(d, A, bgr_dev, bgr_stride, depth_dev, depth_stride);
+    {   // one cluster of kCompactCtas CTAs per frame
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(fn * kCompactCtas));
+        cfg.blockDim = dim3(1024);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kCompactCtas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CVO_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_compact, d, A, bgr_dev, bgr_stride, depth_dev, depth_stride));
+    }
     if (launches) *launches += 9;
     CVO_CUDA_TRY(cudaGetLastError());
     return CVO_OK;
