@@ -88,10 +88,17 @@ struct cvo_handle {
 
 struct cvo_batch {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, sel_stream = nullptr;
     cvo_calib cal;
     cvo_params prm;
     int w = 0, h = 0, max_frames = 0, max_pairs = 0, chunk = 0;
+    // Uploads of host images run beside the alignment of other frames: copies on copy_stream, selection on
+    // sel_stream.  A consumer on `stream` waits for the uploads whose frame range it touches; an upload waits for
+    // the consumers of the frames it overwrites (compute_done covers everything enqueued on `stream` so far).
+    struct Upload { int lo = 0, hi = 0; cudaEvent_t ev = nullptr; bool valid = false; } up[2];
+    int up_next = 0;
+    int busy_lo = 0, busy_hi = 0;         // frames referenced by work on `stream` since the last upload that waited
+    cudaEvent_t compute_done = nullptr;
     CloudArena arena;
     SelWorkspace *sel[2] = {nullptr, nullptr};
     cudaEvent_t sel_done[2] = {nullptr, nullptr}, ev0 = nullptr, ev1 = nullptr, ev_user[2] = {nullptr, nullptr};
@@ -113,6 +120,29 @@ struct cvo_batch {
 };
 
 static const int kPinnedBytes = 1 << 16;
+
+// before enqueuing work on b->stream that touches frames [lo, hi)
+static int batch_consume(cvo_batch *b, int lo, int hi) {
+    for (int u = 0; u < 2; u++)
+        if (b->up[u].valid && b->up[u].lo < hi && lo < b->up[u].hi) CVO_CUDA_TRY(cudaStreamWaitEvent(b->stream, b->up[u].ev, 0));
+    if (b->busy_hi <= b->busy_lo) { b->busy_lo = lo; b->busy_hi = hi; }
+    else { if (lo < b->busy_lo) b->busy_lo = lo; if (hi > b->busy_hi) b->busy_hi = hi; }
+    return CVO_OK;
+}
+// after enqueuing it
+static int batch_consumed(cvo_batch *b) {
+    CVO_CUDA_TRY(cudaEventRecord(b->compute_done, b->stream));
+    return CVO_OK;
+}
+static void pair_frame_range(const cvo_pair_desc *pairs, int n, int &lo, int &hi) {
+    lo = 1 << 30; hi = -1;
+    for (int i = 0; i < n; i++) {
+        const int a = pairs[i].fixed_frame < pairs[i].moving_frame ? pairs[i].fixed_frame : pairs[i].moving_frame;
+        const int c = pairs[i].fixed_frame > pairs[i].moving_frame ? pairs[i].fixed_frame : pairs[i].moving_frame;
+        if (a < lo) lo = a;
+        if (c + 1 > hi) hi = c + 1;
+    }
+}
 
 // k_query reports "this cloud was truncated (selection overflow, or larger than the align scratch)" by
 // returning -1 - count: restore the counts, tell the caller
@@ -755,6 +785,9 @@ int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int devic
     if (rc == CVO_OK) {
         e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->sel_stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->up[i].ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->compute_done, cudaEventDisableTiming);
         for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&b->sel_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
@@ -798,15 +831,30 @@ int cvo_batch_destroy(cvo_batch *b) {
     for (int i = 0; i < 2; i++) if (b->ev_user[i]) cudaEventDestroy(b->ev_user[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
     if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    if (b->sel_stream) cudaStreamDestroy(b->sel_stream);
+    for (int i = 0; i < 2; i++) if (b->up[i].ev) cudaEventDestroy(b->up[i].ev);
+    if (b->compute_done) cudaEventDestroy(b->compute_done);
     delete b;
     return CVO_OK;
 }
 
 // Host images: chunks alternate between two staging workspaces so that the H2D copy of chunk
-// c+1 (copy stream) overlaps the selection kernels of chunk c (compute stream).
+// c+1 (copy stream) overlaps the selection kernels of chunk c (selection stream).  The call only enqueues:
+// it returns while the copies are in flight (the host images must stay valid until a call that consumes
+// these frames has returned), and neither stream is ordered behind the alignment of OTHER frames — a caller
+// that uploads the frames of step k+1 into a second range of the arena before it aligns step k has the
+// upload run beside that alignment.
 int cvo_batch_set_frames(cvo_batch *b, int first, int n, const uint8_t *bgr, const uint16_t *depth) {
     if (!b || !bgr || !depth || first < 0 || n < 0 || first + n > b->max_frames) return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
+    if (n == 0) return CVO_OK;
+    if (b->busy_lo < first + n && first < b->busy_hi) {   // these frames are being read: behind everything enqueued so far
+        CVO_CUDA_TRY(cudaStreamWaitEvent(b->sel_stream, b->compute_done, 0));
+        b->busy_lo = b->busy_hi = 0;
+    }
+    cvo_batch::Upload &up = b->up[b->up_next & 1];
+    b->up_next++;
+    if (up.valid) CVO_CUDA_TRY(cudaStreamWaitEvent(b->sel_stream, up.ev, 0));   // (same stream: keeps the slot's meaning simple)
     const size_t fb = (size_t)b->w * b->h * 3, fd = (size_t)b->w * b->h;
     int ci = 0;
     cudaEvent_t copied;
@@ -822,12 +870,14 @@ int cvo_batch_set_frames(cvo_batch *b, int first, int n, const uint8_t *bgr, con
         CVO_CUDA_TRY(cudaMemcpy2DAsync(sel_depth_ptr(ws, 0), dstride, depth + (size_t)off * fd, fd * 2, fd * 2, m,
                                        cudaMemcpyHostToDevice, b->copy_stream));
         CVO_CUDA_TRY(cudaEventRecord(copied, b->copy_stream));
-        CVO_CUDA_TRY(cudaStreamWaitEvent(b->stream, copied, 0));
-        int rc = sel_run(ws, m, nullptr, nullptr, b->cal, b->prm, b->arena, first + off, b->stream, &b->launches);
+        CVO_CUDA_TRY(cudaStreamWaitEvent(b->sel_stream, copied, 0));
+        int rc = sel_run(ws, m, nullptr, nullptr, b->cal, b->prm, b->arena, first + off, b->sel_stream, &b->launches);
         if (rc != CVO_OK) { cudaEventDestroy(copied); return rc; }
-        CVO_CUDA_TRY(cudaEventRecord(b->sel_done[ci & 1], b->stream));
+        CVO_CUDA_TRY(cudaEventRecord(b->sel_done[ci & 1], b->sel_stream));
     }
     cudaEventDestroy(copied);
+    up.lo = first; up.hi = first + n; up.valid = true;
+    CVO_CUDA_TRY(cudaEventRecord(up.ev, b->sel_stream));
     return CVO_OK;
 }
 
@@ -835,19 +885,26 @@ int cvo_batch_set_frames_device(cvo_batch *b, int first, int n, const uint8_t *b
     if (!b || !bgr_dev || !depth_dev || first < 0 || n < 0 || first + n > b->max_frames) return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
     const size_t fb = (size_t)b->w * b->h * 3, fd = (size_t)b->w * b->h;
+    if (n == 0) return CVO_OK;
+    int rc0 = batch_consume(b, first, first + n);   // (a writer on the compute stream: ordered like a consumer)
+    if (rc0 != CVO_OK) return rc0;
+    // the selection workspace is shared with the uploads of host images
+    for (int u = 0; u < 2; u++) if (b->up[u].valid) CVO_CUDA_TRY(cudaStreamWaitEvent(b->stream, b->up[u].ev, 0));
     for (int off = 0; off < n; off += b->chunk) {
         const int m = (n - off) < b->chunk ? (n - off) : b->chunk;
         int rc = sel_run(b->sel[0], m, bgr_dev + (size_t)off * fb, depth_dev + (size_t)off * fd, b->cal, b->prm,
                          b->arena, first + off, b->stream, &b->launches);
         if (rc != CVO_OK) return rc;
     }
-    return CVO_OK;
+    CVO_CUDA_TRY(cudaEventRecord(b->sel_done[0], b->stream));   // (sel[0]'s staging / scratch is busy until here)
+    return batch_consumed(b);
 }
 
 int cvo_batch_frame_size(cvo_batch *b, int frame, int *n) {
     if (!b || !n || frame < 0 || frame >= b->max_frames) return CVO_ERR_INVALID;
     CVO_CUDA_TRY(cudaSetDevice(b->device));
     int ovf = 0;
+    { int rc = batch_consume(b, frame, frame + 1); if (rc != CVO_OK) return rc; }
     CVO_CUDA_TRY(cudaMemcpyAsync(n, b->arena.n + frame, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaMemcpyAsync(&ovf, b->arena.ovf + frame, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -869,11 +926,18 @@ int cvo_batch_align(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, cvo_a
         memcpy(t.T, p.T, sizeof(t.T));
         t.ell = p.ell;
     }
+    {
+        int lo, hi;
+        pair_frame_range(pairs, n_pairs, lo, hi);
+        int rc = batch_consume(b, lo, hi);
+        if (rc != CVO_OK) return rc;
+    }
     CVO_CUDA_TRY(cudaMemcpyAsync(b->d_tasks, b->h_tasks, sizeof(AlignTask) * n_pairs, cudaMemcpyHostToDevice, b->stream));
     CVO_CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
     int rc = align_run(b->aws, b->prm, n_pairs, b->d_tasks, b->d_results, nullptr, 0, false, b->stream, &b->launches);
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+    { int rc2 = batch_consumed(b); if (rc2 != CVO_OK) return rc2; }
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, sizeof(cvo_align_result) * n_pairs, cudaMemcpyDeviceToHost,
                                  b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -898,8 +962,16 @@ int cvo_batch_inner_product(cvo_batch *b, int n_pairs, const cvo_pair_desc *pair
         q.ell = results[i].ell;
         q.kind = 0;
     }
+    {
+        int lo, hi;
+        pair_frame_range(pairs, n_pairs, lo, hi);
+        int rc0 = batch_consume(b, lo, hi);
+        if (rc0 != CVO_OK) return rc0;
+    }
     CVO_CUDA_TRY(cudaMemcpyAsync(b->d_q, b->h_q, sizeof(QueryTask) * n_pairs, cudaMemcpyHostToDevice, b->stream));
     int rc = query_run(b->aws, b->prm, n_pairs, b->d_q, b->d_qo, b->stream, &b->launches);
+    if (rc != CVO_OK) return rc;
+    rc = batch_consumed(b);
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_qo, b->d_qo, sizeof(QueryOut) * n_pairs, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaStreamSynchronize(b->stream));
@@ -979,11 +1051,18 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs, c
         self_fx[i] = self_task(pairs[i].fixed_frame, results[i].ell);
         self_mv[i] = self_task(pairs[i].moving_frame, results[i].ell);
     }
+    {
+        int lo, hi;
+        pair_frame_range(pairs, n_pairs, lo, hi);
+        int rc0 = batch_consume(b, lo, hi);
+        if (rc0 != CVO_OK) return rc0;
+    }
     CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lc, b->h_lc, sizeof(LcTask) * n_pairs, cudaMemcpyHostToDevice, b->stream));
     CVO_CUDA_TRY(cudaMemcpyAsync(b->d_lcq, b->h_lcq, sizeof(QueryTask) * nq, cudaMemcpyHostToDevice, b->stream));
     int rc = lc_run(b->aws, b->prm, n_pairs, b->d_lc, b->d_lco, b->stream, &b->launches);
     if (rc != CVO_OK) return rc;
     rc = query_run(b->aws, b->prm, nq, b->d_lcq, b->d_lcqo, b->stream, &b->launches);
+    if (rc == CVO_OK) rc = batch_consumed(b);
     if (rc != CVO_OK) return rc;
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lco, b->d_lco, sizeof(LcOut) * n_pairs, cudaMemcpyDeviceToHost, b->stream));
     CVO_CUDA_TRY(cudaMemcpyAsync(b->h_lcqo, b->d_lcqo, sizeof(QueryOut) * nq, cudaMemcpyDeviceToHost, b->stream));
