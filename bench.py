@@ -18,7 +18,10 @@ round-1 variant (every rank its own F frames / P pairs) and is reported as a sid
 
 `value`: inputs resident in HBM when the timed region starts, timed with CUDA events on the
 stream the kernels run on.  `e2e`: the same step through the C ABI with HOST (pinned) images,
-H2D of every frame and D2H of every result inside the timed region.
+H2D of every frame and D2H of every result inside the timed region; every step uploads its own
+frames, and the upload of step k+1 is enqueued (cvo_batch_set_frames only enqueues) into the other
+half of the arena before step k is aligned, so it runs beside that alignment.  All K uploads, the
+first one included, are inside the timed region.
 """
 from __future__ import annotations
 
@@ -519,6 +522,9 @@ def main():
                 return r, v
 
             def run_host(k_steps):
+                rk = vk = None
+                if k_steps < 1:
+                    return rk, vk
                 upload(0)
                 for k in range(k_steps):
                     if k + 1 < k_steps:
@@ -604,7 +610,7 @@ def main():
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz * 1e6 / 1e12
 
-    def roofline_of(evals, nnz_it, iters, align_ms, ms_step, exp_mode, phases, pairs_here):
+    def roofline_of(evals, nnz_it, iters, align_ms, ms_step, exp_mode, phases, pairs_here, cum_iters):
         flops = evals * FLOP_PER_EVAL + nnz_it * FLOP_PER_NNZ_ITER
         achieved = flops / (align_ms * 1e-3) / 1e12
         traffic, traffic_src = committed_ncu_traffic(n_frames, a.partners, exp_mode) if pairs_here == n_pairs else (None, None)
@@ -626,10 +632,15 @@ def main():
                         frac=traffic / (align_ms * 1e-3) / 1e9 / hbm_peak, peak_source=hbm_src,
                         note="neighbour / verdict lists streamed per iteration (see DESIGN section 3), not algorithmic bytes: "
                              "the clouds themselves are 0.2 MB per pair"),
-                    phase_share={k: round(v / max(1, sum(v2 for k2, v2 in phases.items() if k2 != "rebuilds")), 4)
-                                 for k, v in phases.items() if k != "rebuilds"})
+                    phase_share={k: round(v / max(1, sum(v2 for k2, v2 in phases.items() if k2 not in ("rebuilds", "filters"))), 4)
+                                 for k, v in phases.items() if k not in ("rebuilds", "filters")},
+                    list_builds_per_pair=dict(
+                        searches=round(phases["rebuilds"] / max(1, cum_iters) * iters / max(pairs_here, 1), 2),
+                        filters=round(phases["filters"] / max(1, cum_iters) * iters / max(pairs_here, 1), 2),
+                        note="neighbour-list constructions per alignment: grid searches, and filters of the current list at a "
+                             "length-scale change (DESIGN section 5)"))
 
-    roofline = roofline_of(evals, nnz_it, iters, align_ms, m["ms_step"], a.exp_mode, m["phases"], my_pairs)
+    roofline = roofline_of(evals, nnz_it, iters, align_ms, m["ms_step"], a.exp_mode, m["phases"], my_pairs, s1["iterations"])
     if world > 1:
         roofline["note"] = "rank 0's launch (its block of the list)"
     line = dict(metric="cvo_frame_pair_alignments_per_s", value=value, unit="alignments/s", n_gpus=world,
@@ -683,7 +694,7 @@ def main():
         f0, f1 = fm["stats0"], fm["stats1"]
         key = "roofline_fast" if other == 1 else "roofline_exact"
         line[key] = roofline_of((f1["evals"] - f0["evals"]) / 2, (f1["nnz"] - f0["nnz"]) / 2, (f1["iterations"] - f0["iterations"]) / 2,
-                                fm["align_ms"], fm["ms_step"], other, fm["phases"], n_pairs)
+                                fm["align_ms"], fm["ms_step"], other, fm["phases"], n_pairs, f1["iterations"])
         line[key]["value_alignments_per_s"] = n_pairs / (fm["ms_step"] * 1e-3)
         fm["bt"].close()
         line["single_pair"] = single_pair_legs(api, sm_mhz)

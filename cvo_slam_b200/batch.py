@@ -42,6 +42,8 @@ class Batch:
         depth = np.ascontiguousarray(depth, dtype=np.uint16)
         n = bgr.shape[0]
         assert bgr.shape == (n, self.h, self.w, 3) and depth.shape == (n, self.h, self.w)
+        # the call only enqueues the copies: the arrays must outlive it (until a consuming call has returned)
+        self._keep = getattr(self, "_keep", [])[-3:] + [(bgr, depth)]
         self.api._check(self.lib.cvo_batch_set_frames(self.b, first, n, bgr.ctypes.data,
                                                       depth.ctypes.data), "batch_set_frames")
 
@@ -114,7 +116,7 @@ class Batch:
         s = (C.c_int64 * 8)()
         self.lib.cvo_batch_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         self.api._check(self.lib.cvo_batch_phase_cycles(self.b, s), "batch_phase_cycles")
-        names = ["grid", "P0", "P1a_search", "P1b", "P2", "P3", "P1a_ck", "rebuilds"]
+        names = ["grid", "P0", "P1a_search", "P1b", "P2", "P3", "filters", "rebuilds"]
         return {k: int(s[i]) for i, k in enumerate(names)}
 
     def mark(self, which):

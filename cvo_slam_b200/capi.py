@@ -360,7 +360,7 @@ class CudaLowLevel(LowLevel):
         s = (C.c_int64 * 8)()
         self.lib.cvo_handle_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         self._check(self.lib.cvo_handle_phase_cycles(h, s), "handle_phase_cycles")
-        return dict(zip(("grid", "P0", "P1a", "P1b", "P2", "P3", "P1a_ck", "rebuilds"), [int(x) for x in s]))
+        return dict(zip(("grid", "P0", "P1a", "P1b", "P2", "P3", "filters", "rebuilds"), [int(x) for x in s]))
 
     def compute_innerproduct(self, h, tran):
         """cvo_compute_innerproduct: ((value, num) x 4, H, inliers) in one launch"""

@@ -210,7 +210,12 @@ int cvo_batch_create(const cvo_calib *calib, const cvo_params *params, int devic
                      int max_frames, int max_pairs, int width, int height, cvo_batch **out);
 int cvo_batch_destroy(cvo_batch *b);
 /* point selection + features for n frames starting at frame index `first`;
- * images are n tightly packed BGR8 / depth u16 planes. */
+ * images are n tightly packed BGR8 / depth u16 planes.
+ * The host variant only ENQUEUES (H2D copies on a copy stream, selection on a selection stream) and returns:
+ * the images must stay valid until a call that consumes these frames (align / inner_product / verify_lc /
+ * frame_size) has returned.  It is not ordered behind work on OTHER frames, so a caller that creates the batch
+ * with room for two sets of frames can upload the frames of step k+1 while step k is being aligned; a call
+ * that overwrites frames still in use waits for their consumers. */
 int cvo_batch_set_frames(cvo_batch *b, int first, int n, const uint8_t *bgr,
                          const uint16_t *depth);
 int cvo_batch_set_frames_device(cvo_batch *b, int first, int n, const uint8_t *bgr_dev,

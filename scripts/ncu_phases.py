@@ -48,6 +48,10 @@ rows = list(csv.reader(csvtxt.splitlines()))
 hdrs = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 i0 = hdrs[0]; hdr = rows[i0]; data = rows[i0 + 1:]
 ca, cs, ci, ct = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+STALLS = ["stall_barrier", "stall_branch_resolving", "stall_dispatch", "stall_lg", "stall_long_sb", "stall_math", "stall_mio", "stall_no_inst",
+          "stall_not_selected", "stall_selected", "stall_short_sb", "stall_wait", "stall_sleep", "stall_membar", "stall_drain", "stall_misc", "stall_tex"]
+cst = [hdr.index(n) for n in STALLS]
+stl = {}
 base = None; agg = {}; cur = "setup"; tot = [0, 0, 0]; ops = {}
 for r in data:
     if len(r) <= ct or not r[ci].isdigit(): continue
@@ -57,6 +61,8 @@ for r in data:
     if p: cur = p
     s, n, tn = int(r[cs] or 0), int(r[ci]), int(r[ct])
     d = agg.setdefault(cur, [0, 0, 0]); d[0] += s; d[1] += n; d[2] += tn
+    sv = stl.setdefault(cur, [0] * len(STALLS))
+    for q, c in enumerate(cst): sv[q] += int(r[c] or 0)
     tot[0] += s; tot[1] += n; tot[2] += tn
     op = addr2op.get(a - base, "?").split()[0]
     if op.startswith("@"): op = addr2op[a - base].split()[1]
@@ -66,7 +72,9 @@ print(f"total samples {tot[0]} warp-instr {tot[1]} thread-instr {tot[2]}")
 for name, _ in marks:
     if name in agg:
         s, n, tn = agg[name]
-        print(f"{name:14s} {100*s/tot[0]:5.1f}% smp {100*n/tot[1]:5.1f}% ins  thr/ins {tn/max(n,1):4.1f}  smp/ins {s/max(n,1)*tot[1]/tot[0]:4.2f}")
+        sv = stl[name]; top = sorted(range(len(STALLS)), key=lambda q: -sv[q])[:5]
+        print(f"{name:14s} {100*s/tot[0]:5.1f}% smp {100*n/tot[1]:5.1f}% ins  thr/ins {tn/max(n,1):4.1f}  smp/ins {s/max(n,1)*tot[1]/tot[0]:4.2f}  " +
+              " ".join(f"{STALLS[q][6:]}:{100*sv[q]/max(sum(sv),1):.0f}%" for q in top))
 if len(sys.argv) > 3:
     for ph in sys.argv[3:]:
         print("--", ph)

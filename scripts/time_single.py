@@ -27,7 +27,7 @@ for mode in (0, 1):
     for r in range(reps):
         api.inner_product(h, 1, res.transform_np(), 0)
     tq = (time.perf_counter() - t0) / reps
-    ph = api.phase_cycles(h); rb = ph.pop("rebuilds"); tot = sum(ph.values()); print("   rebuilds (all runs of this handle):", rb, "iterations", s1["iterations"])
+    ph = api.phase_cycles(h); rb = (ph.pop("rebuilds"), ph.pop("filters")); tot = sum(ph.values()); print("   (searches, filters) over all runs of this handle:", rb, "iterations", s1["iterations"])
     print("   phase cycles per iteration:", {k: round(v / max(s1["iterations"], 1)) for k, v in ph.items()}, "total", round(tot / max(s1["iterations"], 1)))
     print(f"exp_mode {mode}: N={n} iterations {res.iterations} evals {s1['evals']-s0['evals']} nnz_sum {s1['nnz']-s0['nnz']} "
           f"align ms min {min(ts)*1e3:.3f} med {sorted(ts)[len(ts)//2]*1e3:.3f} -> {min(ts)*1e6/res.iterations:.1f} us/iter; "

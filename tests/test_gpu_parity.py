@@ -457,6 +457,64 @@ def test_batch_matches_single_and_oracle(cuda_api, oracle_api, tum_calib):
     bt.close()
 
 
+def test_batch_pipelined_uploads_match_plain(cuda_api, tum_calib):
+    """cvo_batch_set_frames only enqueues: the frames of the next step can be uploaded into a second range of
+    the arena before the current step is aligned.  Every step must give the bits of a plain
+    upload-then-align batch, also when a range is overwritten right after it was aligned out of."""
+    from cvo_slam_b200 import batch as B, synth
+    scene = synth.make_scene(8)
+    rng = np.random.default_rng(8)
+    n = 3
+    sets = []
+    for s_ in range(3):   # three different sets of n frames
+        poses = [synth.pose()] + [synth.pose(rng.normal(0, 6e-3, 3), rng.normal(0, 8e-3, 3)) for _ in range(n - 1)]
+        fr = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=100 + 10 * s_ + k)) for k, P in enumerate(poses)]
+        sets.append((np.ascontiguousarray(np.stack([f[0] for f in fr])), np.ascontiguousarray(np.stack([f[1] for f in fr]))))
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    plain = []
+    bt = B.Batch(tum_calib, max_frames=n, max_pairs=len(pairs), width=640, height=480)
+    for bgr, dep in sets:
+        bt.set_frames(bgr, dep)
+        r = bt.align(pairs)
+        v, c = bt.inner_product(pairs, r)
+        plain.append((r["transform"].copy(), r["iterations"].copy(), np.array(v), np.array(c)))
+    bt.close()
+    assert not np.array_equal(plain[0][0], plain[1][0])
+    bt = B.Batch(tum_calib, max_frames=2 * n, max_pairs=len(pairs), width=640, height=480)
+    bank = [pairs, [(f + n, m + n) for f, m in pairs]]
+    bt.set_frames(*sets[0], first=0)
+    for k in range(3):
+        if k + 1 < 3:
+            bt.set_frames(*sets[k + 1], first=((k + 1) & 1) * n)   # set 2 overwrites the range set 0 was just aligned out of
+        r = bt.align(bank[k & 1])
+        v, c = bt.inner_product(bank[k & 1], r)
+        assert all(x == 0 for x in r["status"])
+        assert np.array_equal(r["transform"], plain[k][0]) and np.array_equal(r["iterations"], plain[k][1]), k
+        assert np.array_equal(np.array(v), plain[k][2]) and np.array_equal(np.array(c), plain[k][3]), k
+        assert all(bt.frame_size((k & 1) * n + j) > 1000 for j in range(n))
+    bt.close()
+
+
+def test_list_filter_path_is_exercised(cuda_api, tum_calib, pair_c1):
+    """The C1 alignment changes its length scale three times; with the default skin at least one of the new
+    neighbour lists is derived by filtering the current one — the parity tests above therefore
+    cover that path.  Counters: cvo_handle_phase_cycles[6] = filters, [7] = grid searches."""
+    a, da, b, db, _ = pair_c1
+    for mode in (0, 1):
+        p = cuda_api.default_params()
+        p.exp_mode = mode
+        h = cuda_api.create(tum_calib, p)
+        cuda_api.set_frame(h, 0, a, da)
+        cuda_api.set_frame(h, 1, b, db)
+        res, _ = cuda_api.align(h)
+        ph = cuda_api.phase_cycles(h)
+        csize = 16   # a handle runs a cluster: every CTA counts its own list constructions
+        assert res.status == 0
+        assert ph["filters"] >= 1 and ph["rebuilds"] >= 1, ph
+        assert (ph["filters"] + ph["rebuilds"]) <= 12 * csize, ph
+        cuda_api.destroy(h)
+
+
 def test_tracking_sequence_parity(cuda_api, oracle_api, tum_calib):
     """C2 in miniature: the LocalTracker call pattern over 6 frames, two cvo objects with
     persistent R/T/ell, GPU vs oracle."""
