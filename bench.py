@@ -217,11 +217,12 @@ def cpu_leg(pairs, poses, R0, T0, seed, n_pairs, steps, warmup, device, partners
 
 def committed_ncu_traffic(n_frames, partners, exp_mode):
     """DRAM bytes (read + write) of one k_align_batch launch from the committed `ncu --set full` summary of
-    THIS workload (profiles/r01_align_batch_v8_full_8192pairs.txt: bench.py defaults), or None for any
-    other configuration — a number taken under the profiler is never scaled to another size."""
-    if (n_frames, partners, exp_mode) != (1024, 8, 0):
+    THIS workload and mode (profiles/r02z_align_batch_{exact,fast}_full.txt: bench.py defaults, 8 192 pairs),
+    or None for any other configuration — a number taken under the profiler is never scaled to another size."""
+    if (n_frames, partners) != (1024, 8) or exp_mode not in (0, 1):
         return None, None
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_align_batch_v8_full_8192pairs.txt")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                        "r02z_align_batch_%s_full.txt" % ("exact" if exp_mode == 0 else "fast"))
     try:
         txt = open(path).read()
     except OSError:
