@@ -23,7 +23,7 @@ for m in 0 1; do
     python scripts/ncu_summary.py $rep "ncu --set full --clock-control none, k_align_batch<$name>, the bench's launch: 8192 pairs over 1024 frames (launch 4: after 3 warm-up steps)" > $out/${tag}_align_batch_${name}_full.txt 2>&1
     python scripts/ncu_phases.py $rep k_align_batchILb$((1 - m)) "P1b" "P2 entries" > $out/${tag}_align_batch_${name}_phases.txt 2>&1
     sz=$(stat -c %s $rep)
-    [ $sz -gt 25000000 ] && rm -f $rep
+    if [ $sz -gt 25000000 ]; then rm -f $rep; fi
   fi
 done
 ls -la $out > $out/${tag}_ls.txt

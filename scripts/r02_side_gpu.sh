@@ -18,5 +18,5 @@ rep=$out/${tag}_c3_coop.ncu-rep
 if [ -f $rep ]; then
   python scripts/ncu_summary.py $rep "ncu --set full --clock-control none, k_align_coop<exact>: C3 dense pair (18 k points per cloud), one alignment on a cooperative grid of 128 CTAs" > $out/${tag}_c3_coop_full.txt 2>&1
   python scripts/ncu_phases.py $rep k_align_coopILb1 > $out/${tag}_c3_coop_phases.txt 2>&1
-  [ $(stat -c %s $rep) -gt 25000000 ] && rm -f $rep
+  if [ $(stat -c %s $rep) -gt 25000000 ]; then rm -f $rep; fi
 fi
