@@ -14,7 +14,7 @@ body0 = find("__device__ void align_one(")
 marks = [("setup", body0), ("grid", find("if (sh.do_grid) {", body0)), ("P1a filter", find("---- filter: the list of a smaller length scale", body0)), ("P1a search", find("const int tile = q * csize + crank;", body0)),
          ("P1a ck+prune", find("colour kernel of the tile's raw hits", body0)), ("sort rows", find("---- columns sorted by entry count", body0)),
          ("tile widths", find("tile widths (steps of 32 entries)", body0)), ("pads+scatter", find("pads of the tiles, then the kept entries", body0)),
-         ("P1b", find("---------------- P1b", body0)), ("P1b tiles", find("for (int rr = 0; rr * wpc < nT; rr++)", body0)), ("reduce1+omega", find("wg_reduce_i64<kMode>(sh);", body0)),
+         ("P1b", find("---------------- P1b", body0)), ("P1b tiles", find("while (Tcur < nT) {", body0)), ("reduce1+omega", find("wg_reduce_i64<kMode>(sh);", body0)),
          ("P2 rows", find("---------------- P2", body0)), ("P2 entries", find("float fB = 0.f, fC = 0.f", body0)), ("P2 tiles", find("the warp's next tile: its row data into registers, its verdicts into L2", body0)),
          ("reduce2", find("wg_reduce_dd4<kMode>(bc, sh);", body0)), ("P3", find("---------------- P3", body0)),
          ("epilogue", find("if (kMode == 2) {   // gather the overflow flags", body0))]
