@@ -4,7 +4,8 @@ import csv, os, re, subprocess, sys, tempfile
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(ROOT, "cvo_slam_b200", "libcvo_b200.so")
+so = os.environ.get("CVO_B200_LIB") or os.path.join(ROOT, "cvo_slam_b200", "libcvo_b200.so")   # the build the report was taken on
+CSRC = os.environ.get("CVO_B200_CSRC") or os.path.join(ROOT, "cvo_slam_b200", "csrc")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 addr2line = {}
@@ -45,7 +46,7 @@ print("kernel:", names[k][:100]); print("total samples", tot_s, "warp instr", to
 src = {}
 def text(line):
     if not line: return ""
-    f = os.path.join(ROOT, "cvo_slam_b200", "csrc", line[0])
+    f = os.path.join(CSRC, line[0])
     if f not in src:
         try: src[f] = open(f).read().splitlines()
         except Exception: src[f] = []
