@@ -270,3 +270,25 @@ def test_prev_and_accum_transform_follow_the_last_iteration(oracle_api):
     assert np.array_equal(c.accum_transform, want)
     c.close()
     c2.close()
+
+
+def test_bench_roofline_sources_are_committed():
+    """bench.py quotes the DRAM traffic of its dominant kernel from committed `ncu --set full` summaries of the very
+    workload it runs by default, and from nowhere else: the files exist, parse, name the kernel, and any other
+    configuration gets no traffic figure (a number taken under the profiler is never scaled to another size)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for mode, kernel in ((0, "k_align_batch<1>"), (1, "k_align_batch<0>")):
+        traffic, src = bench.committed_ncu_traffic(1024, 8, mode)
+        assert traffic and traffic > 1e10, (mode, traffic)
+        path = os.path.join(ROOT, src)
+        assert os.path.exists(path) and kernel in open(path).read()
+    assert bench.committed_ncu_traffic(128, 8, 0) == (None, None)
+    assert bench.committed_ncu_traffic(1024, 4, 1) == (None, None)
+    # the partition of one list of pairs over the ranks covers every pair exactly once
+    from cvo_slam_b200 import parallel
+    for n, world in ((8192, 8), (8192, 3), (10, 4), (3, 8)):
+        parts = [parallel.partition_blocks(n, r, world) for r in range(world)]
+        assert sorted(int(i) for p in parts for i in p) == list(range(n))
