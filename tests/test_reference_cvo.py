@@ -246,3 +246,39 @@ def test_oracle_matches_reference_cvo_golden_c4(oracle_api):
     bits; tests/test_gpu_parity.py::test_align_c4_specified_large_motion)."""
     worst = _check_backend_against_reference_c4(oracle_api)
     print("oracle vs the reference's cvo.cpp on C4:", worst)
+
+
+# ---- the C3 configuration (dense selection: ~18 k points per cloud, up to 1.4 M non-zeros) ------------------------------
+def test_oracle_matches_reference_cvo_golden_c3(oracle_plain):
+    """The dense regime against the reference's own cvo.cpp (tests/golden/refcvo_golden_c3.npz: counts, SHA-256 of the
+    sorted pattern and of the a_ij in that order, omega, v, step at six injected states).  Gates as for C1 / C4: flows
+    2e-6 of the largest component (observed 4.4e-8 with up to 1.4 M non-zeros), step 1e-5."""
+    spec = importlib.util.spec_from_file_location("make_refcvo_golden_c3", os.path.join(GOLDEN, "make_refcvo_golden_c3.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = dict(np.load(os.path.join(GOLDEN, "refcvo_golden_c3.npz")))
+    api = oracle_plain
+    cal, a, da, b, db, T_gt = gen.c3_pair()
+    crc = [int(x.astype(np.uint64).sum()) for x in (a, da, b, db)]
+    assert crc == [int(x) for x in g["input_crc"]], "the C3 pair is not the one the golden vectors were made from"
+    h, _, _ = gen.dense_clouds(api, cal, a, da, b, db)
+    assert [api.slot_size(h, 0), api.slot_size(h, 1)] == g["sizes"].tolist()
+    worst = dict(omega=0.0, v=0.0, step=0.0, nnz=[])
+    for s in range(int(g["n_states"])):
+        rec = api.iteration_at(h, g[f"s{s}/R"], g[f"s{s}/T"], float(g[f"s{s}/ell"]))
+        ij, av, n = api.last_pattern(h, 1 << 23)
+        assert rec["nnz"] == int(g[f"s{s}/nnz"]) == n, s
+        hk, ha = gen.pattern_digest(ij, av)
+        assert np.array_equal(hk, g[f"s{s}/keys_sha256"]), f"state {s}: in-cutoff pattern differs from the reference's"
+        assert np.array_equal(ha, g[f"s{s}/a_sha256"]), f"state {s}: a_ij differ in the last bits"
+        for name in ("omega", "v"):
+            ref = g[f"s{s}/{name}"]
+            d = float(np.abs(rec[name] - ref).max() / np.abs(ref).max())
+            worst[name] = max(worst[name], d)
+            assert d < 2e-6, (s, name, rec[name], ref)
+        ds = abs(rec["step"] - float(g[f"s{s}/step"])) / float(g[f"s{s}/step"])
+        worst["step"] = max(worst["step"], ds)
+        assert ds < 1e-5, (s, rec["step"], float(g[f"s{s}/step"]))
+        worst["nnz"].append(n)
+    api.destroy(h)
+    print("oracle vs the reference's cvo.cpp on C3 (dense):", worst)
