@@ -241,6 +241,7 @@ class RefCvo:
         lib.refcvo_iteration_at.argtypes = [vp, vp, vp, C.c_float, C.POINTER(_RefRecord), C.c_int, vp, vp]
         lib.refcvo_align.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         lib.refcvo_compute_innerproduct.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        lib.refcvo_compute_innerproduct_lc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         lib.refcvo_update_fixed_pcd.argtypes = [vp]
         lib.refcvo_reset_initial.argtypes = [vp, vp, vp]
         lib.refcvo_set_max_iter.argtypes = [vp, C.c_int]
@@ -299,6 +300,16 @@ class RefCvo:
         inl, cos = C.c_int(0), C.c_float(0)
         self.lib.refcvo_compute_innerproduct(self.h, t.ctypes.data, v.ctypes.data, n.ctypes.data, H.ctypes.data, C.byref(inl), C.byref(cos))
         return dict(values=v, nums=n, H=H.reshape(6, 6), inliers=inl.value, cos_angle=cos.value)
+
+    def compute_innerproduct_lc(self, prior_tran, lc_prior_tran, lc_prior_tran_2, lc_tran):
+        """cvo::compute_innerproduct_lc (cvo.cpp:505-561) -> values / nums in the order {inn_prior, inn_lc_prior,
+        inn_lc_pre, inn_lc_post, inn_fixed_pcd, inn_moving_pcd}, post_hessian, the two inlier counts, cos_angle"""
+        t = [np.ascontiguousarray(x, np.float32).reshape(16) for x in (prior_tran, lc_prior_tran, lc_prior_tran_2, lc_tran)]
+        v, n, H = np.zeros(6, np.float32), np.zeros(6, np.int32), np.zeros(36, np.float64)
+        i1, i2, cos = C.c_int(0), C.c_int(0), C.c_float(0)
+        self.lib.refcvo_compute_innerproduct_lc(self.h, t[0].ctypes.data, t[1].ctypes.data, t[2].ctypes.data, t[3].ctypes.data,
+                                                v.ctypes.data, n.ctypes.data, H.ctypes.data, C.byref(i1), C.byref(i2), C.byref(cos))
+        return dict(values=v, nums=n, H=H.reshape(6, 6), inliers_svd=i1.value, inliers_pnpransac=i2.value, cos_angle=cos.value)
 
     def update_fixed_pcd(self):
         self.lib.refcvo_update_fixed_pcd(self.h)

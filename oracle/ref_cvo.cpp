@@ -158,6 +158,25 @@ void refcvo_compute_innerproduct(void *h, const float tran[16], float values[4],
     for (int k = 0; k < 4; k++) { values[k] = r[k]->value; nums[k] = r[k]->num; }
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) H[i * 6 + j] = Hm(i, j);
 }
+// cvo::compute_innerproduct_lc (cvo.cpp:505-561): values / nums = {prior, lc_prior, lc_pre, lc_post, fixed, moving};
+// the four transforms are 4x4 row-major and are applied to the moving cloud
+void refcvo_compute_innerproduct_lc(void *h, const float prior[16], const float lc_prior[16], const float lc_prior_2[16],
+                                    const float lc[16], float values[6], int nums[6], double H[36], int *inliers_svd,
+                                    int *inliers_pnpransac, float *cos_angle) {
+    cvo::cvo *c = static_cast<cvo::cvo *>(h);
+    cvo::inn_p r[6];
+    Eigen::Matrix<double, 6, 6> Hm;
+    Eigen::Affine3f t[4];
+    const float *src[4] = {prior, lc_prior, lc_prior_2, lc};
+    for (int k = 0; k < 4; k++)
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) t[k].matrix()(i, j) = src[k][i * 4 + j];
+    *inliers_svd = 0;
+    *inliers_pnpransac = 0;
+    c->compute_innerproduct_lc(r[0], r[1], r[2], r[3], Hm, t[0], t[1], t[2], t[3], *inliers_svd, *inliers_pnpransac, r[4], r[5],
+                               *cos_angle);
+    for (int k = 0; k < 6; k++) { values[k] = r[k].value; nums[k] = r[k].num; }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) H[i * 6 + j] = Hm(i, j);
+}
 // the state shuffles (cvo.cpp:578-618)
 void refcvo_update_fixed_pcd(void *h) { static_cast<cvo::cvo *>(h)->update_fixed_pcd(); }
 void refcvo_reset_initial(void *h, const float odom[16], float back[16]) {

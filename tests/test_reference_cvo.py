@@ -282,3 +282,37 @@ def test_oracle_matches_reference_cvo_golden_c3(oracle_plain):
         worst["nnz"].append(n)
     api.destroy(h)
     print("oracle vs the reference's cvo.cpp on C3 (dense):", worst)
+
+
+# ---- cvo::compute_innerproduct_lc (cvo.cpp:505-561), the loop-closure verification record -----------------------------
+def _check_lc_against_reference(api, tum_calib, pair_c1, value_rtol):
+    from cvo_slam_b200 import cvo as cvo_mod
+    g = dict(np.load(os.path.join(GOLDEN, "refcvo_golden_lc.npz")))
+    a, da, b, db, _ = pair_c1
+    crc = [int(x.astype(np.uint64).sum()) for x in (a, da, b, db)]
+    assert crc == [int(x) for x in g["input_crc"]], "the C1 pair is not the one the golden vectors were made from"
+    c = cvo_mod.Cvo(tum_calib, api=api)
+    c.set_pcd(a, da)
+    c.set_pcd(b, db)
+    worst = 0.0
+    for s in range(int(g["n_sets"])):
+        api.set_ell(c.h, float(g[f"c{s}/ell"]))
+        r = c.compute_innerproduct_lc(g[f"c{s}/prior"], g[f"c{s}/lc_prior"], g[f"c{s}/lc_prior_2"], g[f"c{s}/lc"])
+        got = [r[k] for k in ("inn_prior", "inn_lc_prior", "inn_lc_pre", "inn_lc_post", "inn_fixed_pcd", "inn_moving_pcd")]
+        for q, gv, gn in zip(got, g[f"c{s}/values"], g[f"c{s}/nums"]):
+            assert q.num == int(gn), (s, q, gn)
+            assert q.value == pytest.approx(float(gv), rel=value_rtol)
+            worst = max(worst, abs(q.value - float(gv)) / float(gv))
+        assert r["inliers_svd"] == int(g[f"c{s}/inliers_svd"]) and r["inliers_pnpransac"] == int(g[f"c{s}/inliers_pnpransac"])
+        assert float(r["cos_angle"]) == pytest.approx(float(g[f"c{s}/cos_angle"]), rel=value_rtol)
+        H = g[f"c{s}/H"]
+        assert np.allclose(r["post_hessian"], H, rtol=0, atol=value_rtol * np.abs(H).max())
+    c.close()
+    return worst
+
+
+def test_oracle_matches_reference_lc_golden(oracle_api, tum_calib, pair_c1):
+    """Three candidate sets at ell 0.10 / 0.06 / 0.03: every pair count and both inlier counts equal, values, cos_angle and
+    the eigenvalue-shifted Hessian to 1e-6."""
+    worst = _check_lc_against_reference(oracle_api, tum_calib, pair_c1, 1e-6)
+    print("oracle vs the reference's compute_innerproduct_lc: worst relative value difference", worst)
