@@ -241,8 +241,9 @@ int cvo_batch_verify_lc(cvo_batch *b, int n_pairs, const cvo_pair_desc *pairs,
 int cvo_batch_stats(cvo_batch *b, int64_t stats[4]);
 int cvo_handle_stats(cvo_handle *h, int64_t stats[4]);
 /* cumulative SM cycles (thread 0 of every CTA) per phase of the align kernel:
- * {grid build, P0 transform, P1a neighbour search, P1b kernel values + flow, P2 step coefficients,
- * P3 scalar update, P1a colour-kernel + pruning pass}, then the number of neighbour-list rebuilds */
+ * {grid build, P0 bookkeeping, P1a neighbour-list construction (search or filter, colour kernel, tiling),
+ * P1b kernel values + flow, P2 step coefficients, P3 scalar update}, then two counters: neighbour lists derived
+ * by filtering the current one, and neighbour lists built by a grid search */
 int cvo_handle_phase_cycles(cvo_handle *h, int64_t cycles[8]);
 int cvo_batch_phase_cycles(cvo_batch *b, int64_t cycles[8]);
 /* device-time of the last cvo_batch_align's kernel in ms (CUDA events on its stream) */
