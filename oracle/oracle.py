@@ -244,6 +244,10 @@ class RefCvo:
         lib.refcvo_compute_innerproduct_lc.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
         lib.refcvo_update_fixed_pcd.argtypes = [vp]
         lib.refcvo_reset_initial.argtypes = [vp, vp, vp]
+        lib.refcvo_update_previous_pcd.argtypes = [vp]
+        lib.refcvo_reset_keyframe.argtypes = [vp, vp]
+        lib.refcvo_reset_transform.argtypes = [vp, vp]
+        lib.refcvo_slot_sizes.argtypes = [vp, vp]
         lib.refcvo_set_max_iter.argtypes = [vp, C.c_int]
         cal = np.array([calib.scaling_factor, calib.fx, calib.fy, calib.cx, calib.cy], np.float32)
         self.h = lib.refcvo_create(cal.ctypes.data)
@@ -319,6 +323,23 @@ class RefCvo:
         back = np.zeros(16, np.float32)
         self.lib.refcvo_reset_initial(self.h, o.ctypes.data, back.ctypes.data)
         return back.reshape(4, 4)
+
+    def update_previous_pcd(self):
+        self.lib.refcvo_update_previous_pcd(self.h)
+
+    def reset_keyframe(self, odom):
+        o = np.ascontiguousarray(odom, np.float32).reshape(16)
+        self.lib.refcvo_reset_keyframe(self.h, o.ctypes.data)
+
+    def reset_transform(self, odom):
+        o = np.ascontiguousarray(odom, np.float32).reshape(16)
+        self.lib.refcvo_reset_transform(self.h, o.ctypes.data)
+
+    def slot_sizes(self):
+        """points in the fixed / moving / previous slot, -1 for an empty (moved-from) slot"""
+        n = np.zeros(3, np.int32)
+        self.lib.refcvo_slot_sizes(self.h, n.ctypes.data)
+        return [int(x) for x in n]
 
     def set_max_iter(self, n):
         self.lib.refcvo_set_max_iter(self.h, int(n))

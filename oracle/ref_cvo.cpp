@@ -186,6 +186,24 @@ void refcvo_reset_initial(void *h, const float odom[16], float back[16]) {
     Eigen::Affine3f b = c->reset_initial(o);
     for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) back[i * 4 + j] = b.matrix()(i, j);
 }
+void refcvo_update_previous_pcd(void *h) { static_cast<cvo::cvo *>(h)->update_previous_pcd(); }
+void refcvo_reset_keyframe(void *h, const float odom[16]) {
+    Eigen::Affine3f o;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) o.matrix()(i, j) = odom[i * 4 + j];
+    static_cast<cvo::cvo *>(h)->reset_keyframe(o);
+}
+void refcvo_reset_transform(void *h, const float odom[16]) {
+    Eigen::Affine3f o;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) o.matrix()(i, j) = odom[i * 4 + j];
+    static_cast<cvo::cvo *>(h)->reset_transform(o);
+}
+// points in the fixed / moving / previous slot (-1 = the slot is empty: its unique_ptr was moved from)
+void refcvo_slot_sizes(void *h, int n[3]) {
+    cvo::cvo *c = static_cast<cvo::cvo *>(h);
+    n[0] = c->ptr_fixed_pcd ? c->ptr_fixed_pcd->num_points : -1;
+    n[1] = c->ptr_moving_pcd ? c->ptr_moving_pcd->num_points : -1;
+    n[2] = c->ptr_previous_pcd ? c->ptr_previous_pcd->num_points : -1;
+}
 void refcvo_set_max_iter(void *h, int n) { static_cast<cvo::cvo *>(h)->MAX_ITER = n; }
 
 }  // extern "C"

@@ -316,3 +316,97 @@ def test_oracle_matches_reference_lc_golden(oracle_api, tum_calib, pair_c1):
     the eigenvalue-shifted Hessian to 1e-6."""
     worst = _check_lc_against_reference(oracle_api, tum_calib, pair_c1, 1e-6)
     print("oracle vs the reference's compute_innerproduct_lc: worst relative value difference", worst)
+
+
+# ---- the state shuffles (cvo.cpp:578-618) driven like the keyframe tracker of LocalTracker ------------------------------
+def test_reference_state_shuffles_live(oracle_api, tum_calib):
+    """Where /root/reference is present: the compiled reference class and the mirror of the drop-in class
+    (cvo_slam_b200/cvo.py: the host logic of include/cvo.hpp, over the oracle) are driven through the same sequence —
+    set_pcd x2, align, update_previous_pcd, set_pcd, align, reset_keyframe (previous -> fixed, moving -> previous),
+    reset_transform, set_pcd, reset_initial, align, reset_keyframe again, update_fixed_pcd — and after every call the
+    three slots hold clouds of the same sizes (an empty slot is a moved-from unique_ptr), the public `transform` is the
+    same, and one iteration body evaluated on the slots gives the same pattern size and flows (i.e. the SAME clouds
+    sit in the fixed / moving slots, not merely clouds of equal size)."""
+    from oracle import oracle
+    from cvo_slam_b200 import cvo as cvo_mod, synth
+    rc = oracle.load_refcvo(tum_calib)
+    if rc is None:
+        pytest.skip("oracle/_ref/libref_cvo.so not built (no /root/reference here)")
+    scene = synth.make_scene(9)
+    poses = synth.trajectory(5, 9)
+    frames = [synth.to_numpy(*synth.render(scene, P, tum_calib, 640, 480, noise_seed=90 + k)) for k, P in enumerate(poses)]
+    p = oracle_api.default_params()
+    p.max_iter = 6   # short alignments: the subject is the bookkeeping around them
+    rc.set_max_iter(6)
+    c = cvo_mod.Cvo(tum_calib, params=p, api=oracle_api)
+    I, z = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+
+    def slots_equal(where):
+        got = [oracle_api.slot_size(c.h, s) for s in range(3)]
+        ref = rc.slot_sizes()
+        assert [max(g, -1) for g in got] == ref, (where, got, ref)
+
+    def same_clouds(where, ell=0.10):
+        Rs, Ts, ells, tfs = rc.get_state()   # (the driver's iteration_at leaves its arguments in the object: put the state back)
+        r1 = rc.iteration_at(I, z, ell)
+        rc.set_state(Rs, Ts, ells)
+        rc.reset_transform(tfs)
+        o1 = oracle_api.iteration_at(c.h, I, z, ell)
+        assert r1["nnz"] == o1["nnz"] and r1["nnz"] > 0, (where, r1["nnz"], o1["nnz"])
+        for name in ("omega", "v"):
+            assert np.abs(r1[name] - o1[name]).max() / np.abs(o1[name]).max() < 2e-6, (where, name)
+
+    def both_align(where):
+        ra = rc.align()
+        c.align()
+        Rr, Tr, ellr, tfr = rc.get_state()
+        Ro, To = oracle_api.get_RT(c.h)
+        # six iterations from the same state: the same bits, or the few ulps of the reference's float row sums
+        assert np.abs(Rr - Ro).max() < 1e-6 and np.abs(Tr - To).max() < 1e-6, where
+        assert ellr == pytest.approx(oracle_api.get_ell(c.h))
+        assert np.abs(ra["transform"] - c.transform).max() < 1e-6, where
+
+    odom_a = synth.pose((0.002, -0.001, 0.003), (0.004, 0.002, -0.003)).astype(np.float32)
+    odom_b = synth.pose((-0.003, 0.002, 0.001), (0.006, -0.004, 0.002)).astype(np.float32)
+    for x in (rc, c):
+        x.set_pcd(*frames[0])
+        x.set_pcd(*frames[1])
+    slots_equal("set_pcd x2")
+    same_clouds("set_pcd x2")
+    both_align("first align")
+    for x in (rc, c):
+        x.update_previous_pcd()          # moving -> previous
+    slots_equal("update_previous_pcd")
+    for x in (rc, c):
+        x.set_pcd(*frames[2])
+    slots_equal("set_pcd 3")
+    both_align("second align")
+    for x in (rc, c):
+        x.reset_keyframe(odom_a)         # previous (frame 1) -> fixed, moving (frame 2) -> previous, transform = odom
+    slots_equal("reset_keyframe")
+    assert np.array_equal(rc.get_state()[3], c.transform) and np.array_equal(c.transform, odom_a)
+    for x in (rc, c):
+        x.set_pcd(*frames[3])
+    slots_equal("set_pcd 4")
+    same_clouds("after reset_keyframe: fixed = frame 1, moving = frame 3")
+    back_r = rc.reset_initial(odom_b)
+    back_o = c.reset_initial(odom_b)
+    assert np.array_equal(back_r, back_o)
+    Rr, Tr, _, _ = rc.get_state()
+    Ro, To = oracle_api.get_RT(c.h)
+    assert np.array_equal(Rr, Ro) and np.array_equal(Tr, To)
+    both_align("third align, from reset_initial")
+    for x in (rc, c):
+        x.reset_transform(odom_b)
+    assert np.array_equal(rc.get_state()[3], c.transform)
+    for x in (rc, c):
+        x.reset_keyframe(odom_a)         # pre_pc_init is set: fixed <- previous (frame 2), previous <- moving (frame 3)
+    slots_equal("second reset_keyframe")
+    for x in (rc, c):
+        x.set_pcd(*frames[4])
+    same_clouds("after the second reset_keyframe: fixed = frame 2, moving = frame 4")
+    for x in (rc, c):
+        x.update_fixed_pcd()             # moving -> fixed
+    slots_equal("update_fixed_pcd")
+    rc.close()
+    c.close()
